@@ -1,0 +1,582 @@
+// gt_build.cu — edge list -> 2DT tiles in TCSC, entirely on the device.
+//
+// Replaces, for this rank (reference paths relative to the GraphTap repo):
+//   Graph::parread_binary     per-edge flags: drop self-loops, acyclic, transpose, mirror   src/mat/graph.hpp:337-356
+//   Matrix::distribute        every rank sees the GLOBAL list and keeps its own tiles        src/mat/matrix.hpp:692-810
+//   Matrix::init_tiles        sort by (col,row) [weighted: see below], adjacent dedup        src/mat/matrix.hpp:537-560, src/ds/triple.hpp:78-98
+//   Matrix::filter_vertices   group-wide non-empty bitmaps I/J + prefix maps IV/JV           src/mat/matrix.hpp:860-1122
+//   TCSC_BASE::populate       JA / IA / A / JC / IR                                          src/ds/compressed_column.hpp:370-417
+//
+// Because each rank scans the whole edge list it can mark EVERY row and column of the matrix, so the
+// row-group / column-group OR-reduce + broadcast of the bitmaps (matrix.hpp:973-1083) needs no
+// communication: the maps come out identical on all ranks of a group by construction.
+//
+// Weighted tiles: the reference sorts by (col, weight) with an unstable std::sort and then drops
+// ADJACENT equal (row,col) pairs, so which heavier duplicates survive is unspecified; the lightest
+// copy of every (row,col) always survives.  Here the order is (col, row, weight) and only the
+// lightest copy is kept, which gives identical min-plus results (min is idempotent) with a
+// deterministic layout.  Unweighted tiles are bit-identical to the reference's.
+#include "gt_graph.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <memory>
+
+namespace gt {
+
+// ---------------------------------------------------------------------------------------------
+// counter-based RMAT stream; must stay bit-identical to graphtap_b200/rmat.py
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct RmatParams {
+    uint64_t base, mul[3], add[3], mask, zero;
+    uint32_t sh, scale;
+    int weighted, enabled;
+};
+
+__host__ __device__ __forceinline__ uint64_t rmat_permute(const RmatParams& P, uint64_t v) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        v = (v * P.mul[r] + P.add[r]) & P.mask;
+        v ^= v >> P.sh;
+    }
+    return v;
+}
+
+static RmatParams make_rmat_params(uint32_t scale, uint64_t seed, int weighted) {
+    RmatParams P{};
+    P.enabled = 1;
+    P.scale = scale;
+    P.weighted = weighted;
+    P.mask = (scale >= 64) ? ~0ull : ((1ull << scale) - 1);
+    P.sh = std::max(1u, scale / 2);
+    uint64_t k = splitmix64(seed * 0x632BE59BD9B4E019ull + 0x1234567ull);
+    for (int r = 0; r < 3; r++) {
+        k = splitmix64(k + (uint64_t) r);
+        P.mul[r] = k | 1ull;
+        P.add[r] = k >> 17;
+    }
+    P.base = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull);
+    P.zero = 0;
+    uint64_t root_pre = (1ull << std::max(1u, scale / 4)) - 1;
+    P.zero = rmat_permute(P, root_pre);
+    return P;
+}
+
+__device__ __forceinline__ void rmat_edge(const RmatParams& P, uint64_t e, uint32_t& src, uint32_t& dst, uint32_t& w) {
+    const uint64_t ctr = P.base + e * 32ull;
+    uint64_t s = 0, d = 0, r = 0;
+    for (uint32_t lvl = 0; lvl < P.scale; lvl++) {
+        uint32_t u;
+        if ((lvl & 1) == 0) { r = splitmix64(ctr + (lvl >> 1)); u = (uint32_t) r; }
+        else u = (uint32_t) (r >> 32);
+        uint32_t sbit = u >= 3264175144u;
+        uint32_t dbit = (u >= 2448131358u && u < 3264175144u) || (u >= 4080218931u);
+        s = (s << 1) | sbit;
+        d = (d << 1) | dbit;
+    }
+    src = (uint32_t) (rmat_permute(P, s) ^ P.zero);
+    dst = (uint32_t) (rmat_permute(P, d) ^ P.zero);
+    w = P.weighted ? (uint32_t) ((splitmix64(ctr + 31) >> 33) % 128ull) + 1u : 1u;
+}
+
+__global__ void k_rmat_generate(RmatParams P, uint64_t first, uint64_t n, uint32_t* out) {
+    const int stride = P.weighted ? 3 : 2;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+        uint32_t s, d, w;
+        rmat_edge(P, first + i, s, d, w);
+        out[i * stride] = s;
+        out[i * stride + 1] = d;
+        if (P.weighted) out[i * stride + 2] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ingest: flags -> (row, col, w) entries -> bitmaps, ownership filter, sort keys
+// ---------------------------------------------------------------------------------------------
+struct IngestParams {
+    uint32_t th, p;
+    int self_loops, acyclic, transpose, directed, weighted;
+    int bw;                          // bits of an in-tile coordinate
+    const int32_t* tile_local;       // [p*p] local tile index (row order) or -1
+    uint8_t* I_all;                  // [p*th] any entry in this row    (count pass only)
+    uint8_t* J_all;                  // [p*th] any entry in this column (count pass only)
+    unsigned long long* counters;    // [0] owned entries, [1] append cursor, [2] out-of-range records
+    uint64_t* keys;                  // fill pass
+    uint32_t* wts;                   // fill pass, weighted
+};
+
+template <bool FILL>
+__device__ __forceinline__ void ingest_emit(const IngestParams& Q, uint32_t r, uint32_t c, uint32_t w, bool valid,
+                                            unsigned long long& local_count) {
+    int t = -1;
+    uint32_t rg = 0, cg = 0;
+    if (valid) {
+        rg = r / Q.th;
+        cg = c / Q.th;
+        t = Q.tile_local[rg * Q.p + cg];
+        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; }
+    }
+    const bool own = valid && t >= 0;
+    if (!FILL) {
+        local_count += own ? 1 : 0;
+    } else {
+        // warp-aggregated append (all 32 lanes reach this point together)
+        const unsigned ballot = __ballot_sync(0xffffffffu, own);
+        if (ballot) {
+            const int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&Q.counters[1], (unsigned long long) __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (own) {
+                const unsigned long long pos = base + __popc(ballot & ((1u << lane) - 1));
+                Q.keys[pos] = ((uint64_t) t << (2 * Q.bw)) | ((uint64_t) (c - cg * Q.th) << Q.bw) | (uint64_t) (r - rg * Q.th);
+                if (Q.weighted) Q.wts[pos] = w;
+            }
+        }
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_ingest(IngestParams Q, RmatParams G, const uint32_t* triples, uint64_t first, uint64_t n) {
+    unsigned long long local_count = 0, bad = 0;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    const uint32_t limit = Q.p * Q.th;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool valid = i < n;
+        uint32_t r = 0, c = 0, w = 1;
+        if (valid) {
+            if (G.enabled) rmat_edge(G, first + i, r, c, w);
+            else if (Q.weighted) { r = triples[i * 3]; c = triples[i * 3 + 1]; w = triples[i * 3 + 2]; }
+            else { const uint2 rc = reinterpret_cast<const uint2*>(triples)[i]; r = rc.x; c = rc.y; }
+            if (r >= limit || c >= limit) { bad++; valid = false; }
+        }
+        if (valid && r == c && !Q.self_loops) valid = false;          // graph.hpp:339-342
+        if (valid && Q.acyclic && c < r) { uint32_t x = r; r = c; c = x; }   // :344-347
+        if (valid && Q.transpose) { uint32_t x = r; r = c; c = x; }          // :349-350
+        ingest_emit<FILL>(Q, r, c, w, valid, local_count);                   // :352
+        if (!Q.directed) ingest_emit<FILL>(Q, c, r, w, valid, local_count);  // :354-357
+    }
+    if (!FILL) {
+        typedef cub::BlockReduce<unsigned long long, 256> BR;
+        __shared__ typename BR::TempStorage tmp;
+        unsigned long long tot = BR(tmp).Sum(local_count);
+        __syncthreads();
+        unsigned long long totbad = BR(tmp).Sum(bad);
+        if (threadIdx.x == 0) {
+            if (tot) atomicAdd(&Q.counters[0], tot);
+            if (totbad) atomicAdd(&Q.counters[2], totbad);
+        }
+    }
+}
+
+__global__ void k_u8_to_u32(const uint8_t* in, uint32_t* out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+// segment slot maps from the global bitmap + its exclusive scan
+__global__ void k_seg_maps(const uint8_t* bits_all, const uint32_t* scan_all, uint32_t seg_base, uint32_t th,
+                           uint8_t* bits, uint32_t* prefix, uint32_t* ids) {
+    const uint32_t s0 = scan_all[seg_base];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        const uint8_t b = bits_all[seg_base + i];
+        bits[i] = b;
+        const uint32_t k = scan_all[seg_base + i] - s0;
+        prefix[i] = b ? k : 0;                    // matrix.hpp:1031-1040
+        if (b) ids[k] = i;                        // compressed_column.hpp:399-416 (JC / IR)
+    }
+}
+
+__global__ void k_tile_bounds(const uint64_t* keys, uint64_t n, int ntiles, int shift, uint64_t* bounds) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const uint64_t target = (uint64_t) t << shift;
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (keys[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    bounds[t] = lo;
+}
+
+// IA[e] = IV[row]                                      compressed_column.hpp:392
+__global__ void k_tile_IA(const uint64_t* keys, uint64_t n, uint64_t row_mask, const uint32_t* IV, uint32_t* IA) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x)
+        IA[e] = IV[(uint32_t) (keys[e] & row_mask)];
+}
+
+// JA[j] = first entry whose column is >= JC[j] (empty columns get JA[j] == JA[j+1])   :381-398
+__global__ void k_tile_JA(const uint64_t* keys, uint64_t n, uint64_t tile_prefix, int bw, const uint32_t* JC, uint32_t ncols, uint32_t* JA) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j <= ncols; j += gridDim.x * blockDim.x) {
+        if (j == ncols) { JA[j] = (uint32_t) n; continue; }
+        const uint64_t target = tile_prefix | ((uint64_t) JC[j] << bw);
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        JA[j] = (uint32_t) lo;
+    }
+}
+
+// chunk_col[k] = column that holds edge k*GT_PUSH_CHUNK (last column with JA[c] <= e)
+__global__ void k_chunk_cols(const uint32_t* JA, uint32_t ncols, uint64_t nnz, uint32_t nchunks, uint32_t* chunk_col) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= nchunks; k += gridDim.x * blockDim.x) {
+        if (k == nchunks) { chunk_col[k] = ncols; continue; }
+        const uint64_t e = (uint64_t) k * GT_PUSH_CHUNK;
+        uint32_t lo = 0, hi = ncols;       // upper_bound over JA[0..ncols)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t) JA[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        chunk_col[k] = lo - 1;
+    }
+}
+
+static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) {
+    uint64_t g = (n + block - 1) / block;
+    uint64_t cap = (uint64_t) sm_count * per_sm;
+    return (int) std::max<uint64_t>(1, std::min(g, cap));
+}
+
+static int bits_for(uint32_t v) {   // bits needed to represent values in [0, v)
+    int b = 1;
+    while (b < 32 && (1ull << b) < v) b++;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int weighted, int on_device,
+                       const RmatParams* gen, uint32_t nvertices, const gt_graph_flags* flags, int compression) {
+    GT_REQUIRE(ctx, "gt_graph_build: ctx is NULL");
+    GT_REQUIRE(flags, "gt_graph_build: flags is NULL");
+    GT_REQUIRE(compression == GT_TCSC || compression == GT_TCSC_CF, "gt_graph_build: only _TCSC_ / _TCSC_CF_ are GPU formats");
+    GT_REQUIRE(gen || triples || ntriples == 0, "gt_graph_build: triples is NULL");
+    GT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<gt_graph> g(new gt_graph());
+    g->ctx = ctx;
+    g->flags = *flags;
+    g->weighted = weighted;
+    g->compression = compression;
+    g->nvertices = nvertices;
+    g->nedges_input = ntriples;
+    g->lay = make_layout(nvertices, ctx->nranks, ctx->rank);
+    const Layout& L = g->lay;
+    const uint32_t p = L.info.nranks, th = L.info.tile_height;
+    const uint64_t nall = (uint64_t) p * th;
+    const int ntiles = (int) L.local_tiles_row_order.size();
+    const int bw = bits_for(th);
+    int bt = 0;
+    while ((1 << bt) < ntiles) bt++;
+    GT_REQUIRE(bt + 2 * bw <= 64, "gt_graph_build: tile coordinates do not fit a 64-bit sort key");
+
+    // ownership table
+    std::vector<int32_t> tile_local((size_t) p * p, -1);
+    for (int k = 0; k < ntiles; k++) tile_local[L.local_tiles_row_order[k]] = k;
+    DevBuf<int32_t> d_tile_local; d_tile_local.alloc(tile_local.size());
+    GT_CUDA(cudaMemcpyAsync(d_tile_local.p, tile_local.data(), tile_local.size() * 4, cudaMemcpyHostToDevice, st));
+
+    DevBuf<uint8_t> I_all, J_all;
+    I_all.alloc(nall); J_all.alloc(nall);
+    GT_CUDA(cudaMemsetAsync(I_all.p, 0, nall, st));
+    GT_CUDA(cudaMemsetAsync(J_all.p, 0, nall, st));
+    DevBuf<unsigned long long> counters; counters.alloc(4);
+    GT_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), st));
+
+    IngestParams Q{};
+    Q.th = th; Q.p = p;
+    Q.self_loops = flags->self_loops; Q.acyclic = flags->acyclic; Q.transpose = flags->transpose; Q.directed = flags->directed;
+    Q.weighted = weighted; Q.bw = bw;
+    Q.tile_local = d_tile_local.p; Q.I_all = I_all.p; Q.J_all = J_all.p; Q.counters = counters.p;
+    RmatParams G{};
+    if (gen) G = *gen;
+
+    // host input is staged through a bounded device buffer
+    const uint64_t rec_words = weighted ? 3 : 2;
+    const uint64_t CH = 1ull << 26;
+    DevBuf<uint32_t> stage;
+    if (!gen && !on_device && ntriples) stage.alloc(std::min(CH, ntriples) * rec_words);
+
+    auto run_pass = [&](bool fill) {
+        for (uint64_t first = 0; first < ntriples; first += CH) {
+            const uint64_t n = std::min(CH, ntriples - first);
+            const uint32_t* src = nullptr;
+            if (!gen) {
+                if (on_device) src = (const uint32_t*) triples + first * rec_words;
+                else {
+                    GT_CUDA(cudaMemcpyAsync(stage.p, (const uint32_t*) triples + first * rec_words, n * rec_words * 4, cudaMemcpyHostToDevice, st));
+                    src = stage.p;
+                }
+            }
+            const int grid = grid_for(n, 256, ctx->sm_count, 16);
+            if (fill) k_ingest<true><<<grid, 256, 0, st>>>(Q, G, src, first, n);
+            else k_ingest<false><<<grid, 256, 0, st>>>(Q, G, src, first, n);
+            ctx->kernel_launches++;
+            GT_CUDA(cudaGetLastError());
+            if (!gen && !on_device) GT_CUDA(cudaStreamSynchronize(st));   // stage is reused
+        }
+    };
+
+    run_pass(false);
+    unsigned long long h_counters[4];
+    GT_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    if (h_counters[2])
+        throw Error(GT_ERR_INVALID, "gt_graph_build: " + std::to_string(h_counters[2]) + " records name a vertex id beyond nvertices");
+    uint64_t nloc = h_counters[0];
+
+    DevBuf<uint64_t> keys, keys_alt;
+    DevBuf<uint32_t> wts, wts_alt;
+    keys.alloc(nloc); keys_alt.alloc(nloc);
+    if (weighted) { wts.alloc(nloc); wts_alt.alloc(nloc); }
+    Q.keys = keys.p; Q.wts = wts.p;
+    run_pass(true);
+    GT_CUDA(cudaStreamSynchronize(st));
+    stage.release();
+
+    // ---- sort (+ dedup) ---------------------------------------------------------------------
+    uint64_t* sorted_keys = keys.p;
+    uint32_t* sorted_wts = wts.p;
+    if (nloc) {
+        DevBuf<uint8_t> tmp;
+        size_t tmp_bytes = 0;
+        const int key_bits = bt + 2 * bw;
+        if (!weighted) {
+            cub::DoubleBuffer<uint64_t> db(keys.p, keys_alt.p);
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, (int64_t) nloc, 0, key_bits, st));
+            tmp.alloc(tmp_bytes);
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, db, (int64_t) nloc, 0, key_bits, st));
+            sorted_keys = db.Current();
+        } else {
+            // stable: by weight first, then by (tile, col, row) -> ascending weight inside every (row,col)
+            cub::DoubleBuffer<uint32_t> dw(wts.p, wts_alt.p);
+            cub::DoubleBuffer<uint64_t> dk(keys.p, keys_alt.p);
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dw, dk, (int64_t) nloc, 0, 32, st));
+            size_t tmp2 = 0;
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, dk, dw, (int64_t) nloc, 0, key_bits, st));
+            tmp.alloc(std::max(tmp_bytes, tmp2));
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dw, dk, (int64_t) nloc, 0, 32, st));
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp2, dk, dw, (int64_t) nloc, 0, key_bits, st));
+            sorted_keys = dk.Current();
+            sorted_wts = dw.Current();
+        }
+        ctx->kernel_launches += 8;
+        if (!flags->parallel_edges) {          // matrix.hpp:552-555 (std::unique on adjacent (row,col))
+            uint64_t* other_k = (sorted_keys == keys.p) ? keys_alt.p : keys.p;
+            uint32_t* other_w = weighted ? ((sorted_wts == wts.p) ? wts_alt.p : wts.p) : nullptr;
+            size_t ub = 0;
+            unsigned long long* d_nsel = counters.p + 3;
+            if (!weighted) {
+                GT_CUDA(cub::DeviceSelect::Unique(nullptr, ub, sorted_keys, other_k, d_nsel, (int64_t) nloc, st));
+                if (ub > tmp.n) tmp.alloc(ub);
+                GT_CUDA(cub::DeviceSelect::Unique(tmp.p, ub, sorted_keys, other_k, d_nsel, (int64_t) nloc, st));
+            } else {
+                GT_CUDA(cub::DeviceSelect::UniqueByKey(nullptr, ub, sorted_keys, sorted_wts, other_k, other_w, d_nsel, (int64_t) nloc, st));
+                if (ub > tmp.n) tmp.alloc(ub);
+                GT_CUDA(cub::DeviceSelect::UniqueByKey(tmp.p, ub, sorted_keys, sorted_wts, other_k, other_w, d_nsel, (int64_t) nloc, st));
+            }
+            ctx->kernel_launches += 2;
+            unsigned long long nsel = 0;
+            GT_CUDA(cudaMemcpyAsync(&nsel, d_nsel, sizeof(nsel), cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            nloc = nsel;
+            sorted_keys = other_k;
+            sorted_wts = other_w;
+        }
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+    g->nnz_local = nloc;
+
+    // ---- index maps ---------------------------------------------------------------------------
+    {
+        DevBuf<uint32_t> scan; scan.alloc(nall + 1);
+        DevBuf<uint8_t> tmp;
+        size_t tb = 0;
+        GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, scan.p, scan.p, (int64_t) (nall + 1), st));
+        tmp.alloc(tb);
+        auto make = [&](const DevBuf<uint8_t>& bits_all, const std::vector<int32_t>& segs, std::vector<SegMaps>& out) {
+            GT_CUDA(cudaMemsetAsync(scan.p + nall, 0, 4, st));
+            k_u8_to_u32<<<grid_for(nall, 256, ctx->sm_count), 256, 0, st>>>(bits_all.p, scan.p, nall);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, scan.p, scan.p, (int64_t) (nall + 1), st));
+            ctx->kernel_launches += 2;
+            out.resize(segs.size());
+            std::vector<uint32_t> ends(segs.size() * 2);
+            for (size_t k = 0; k < segs.size(); k++) {
+                const uint64_t b = (uint64_t) segs[k] * th;
+                GT_CUDA(cudaMemcpyAsync(&ends[2 * k], scan.p + b, 4, cudaMemcpyDeviceToHost, st));
+                GT_CUDA(cudaMemcpyAsync(&ends[2 * k + 1], scan.p + b + th, 4, cudaMemcpyDeviceToHost, st));
+            }
+            GT_CUDA(cudaStreamSynchronize(st));
+            for (size_t k = 0; k < segs.size(); k++) {
+                SegMaps& m = out[k];
+                m.segment = segs[k];
+                m.nnz = ends[2 * k + 1] - ends[2 * k];
+                m.bits.alloc(th); m.prefix.alloc(th); m.ids.alloc(m.nnz);
+                k_seg_maps<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(bits_all.p, scan.p, (uint32_t) ((uint64_t) segs[k] * th), th,
+                                                                          m.bits.p, m.prefix.p, m.ids.p);
+                ctx->kernel_launches++;
+            }
+            GT_CUDA(cudaGetLastError());
+            GT_CUDA(cudaStreamSynchronize(st));
+        };
+        make(I_all, L.local_row_segments, g->rows);
+        make(J_all, L.local_col_segments, g->cols);
+    }
+    I_all.release(); J_all.release();
+
+    // ---- tiles ------------------------------------------------------------------------------------
+    std::vector<uint64_t> bounds(ntiles + 1, 0);
+    if (nloc) {
+        DevBuf<uint64_t> d_bounds; d_bounds.alloc(ntiles + 1);
+        k_tile_bounds<<<1, 128, 0, st>>>(sorted_keys, nloc, ntiles, 2 * bw, d_bounds.p);
+        ctx->kernel_launches++;
+        GT_REQUIRE(ntiles + 1 <= 128, "gt_graph_build: more than 127 local tiles");
+        GT_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.p, (ntiles + 1) * 8, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+    // pool offsets are padded to 4 entries so that every tile's IA / A start 16-byte aligned
+    uint64_t pool = 0;
+    std::vector<uint64_t> pool_off(ntiles);
+    for (int k = 0; k < ntiles; k++) { pool_off[k] = pool; pool += (bounds[k + 1] - bounds[k] + 3) / 4 * 4; }
+    g->IA_pool.alloc(pool);
+    if (weighted) g->A_pool.alloc(pool);
+    g->tiles.resize(ntiles);
+    const uint64_t row_mask = (1ull << bw) - 1;
+    for (int k = 0; k < ntiles; k++) {
+        Tile& T = g->tiles[k];
+        const int kth = L.local_tiles_row_order[k];
+        T.rg = kth / p; T.cg = kth % p;
+        T.row_slot = (uint32_t) L.row_slot_of((int) T.rg);
+        T.col_slot = (uint32_t) L.col_slot_of((int) T.cg);
+        T.offset = pool_off[k];
+        T.nnz = bounds[k + 1] - bounds[k];
+        GT_REQUIRE(T.nnz < (1ull << 32), "gt_graph_build: a tile holds 2^32 or more entries (JA is uint32, compressed_column.hpp:293-296)");
+        const SegMaps& R = g->rows[T.row_slot];
+        const SegMaps& C = g->cols[T.col_slot];
+        T.JA.alloc((size_t) C.nnz + 1);
+        const uint64_t* tk = sorted_keys + bounds[k];
+        if (T.nnz) {
+            k_tile_IA<<<grid_for(T.nnz, 256, ctx->sm_count), 256, 0, st>>>(tk, T.nnz, row_mask, R.prefix.p, g->IA_pool.p + T.offset);
+            ctx->kernel_launches++;
+            if (weighted) GT_CUDA(cudaMemcpyAsync(g->A_pool.p + T.offset, sorted_wts + bounds[k], T.nnz * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        k_tile_JA<<<grid_for((uint64_t) C.nnz + 1, 256, ctx->sm_count), 256, 0, st>>>(tk, T.nnz, (uint64_t) k << (2 * bw), bw, C.ids.p, C.nnz, T.JA.p);
+        const uint32_t nchunks = (uint32_t) ((T.nnz + GT_PUSH_CHUNK - 1) / GT_PUSH_CHUNK);
+        T.chunk_col.alloc((size_t) nchunks + 1);
+        k_chunk_cols<<<grid_for((uint64_t) nchunks + 1, 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, C.nnz, T.nnz, nchunks, T.chunk_col.p);
+        ctx->kernel_launches += 2;
+    }
+    GT_CUDA(cudaGetLastError());
+    GT_CUDA(cudaStreamSynchronize(st));
+
+    // nnz over all ranks
+    g->nnz_global = g->nnz_local;
+    if (ctx->comm) {
+        DevBuf<unsigned long long> v; v.alloc(1);
+        unsigned long long h = g->nnz_local;
+        GT_CUDA(cudaMemcpyAsync(v.p, &h, 8, cudaMemcpyHostToDevice, st));
+        comm_allreduce(ctx->comm, COMM_WORLD, v.p, v.p, 1, CT_U64, CO_SUM, st);
+        GT_CUDA(cudaMemcpyAsync(&h, v.p, 8, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        g->nnz_global = h;
+    }
+    return g.release();
+}
+
+}  // namespace gt
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gt_graph_build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int weighted, int on_device,
+                              uint32_t nvertices, const gt_graph_flags* flags, int compression, gt_graph** out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(out, "gt_graph_build: out is NULL");
+        *out = gt::build(ctx, triples, ntriples, weighted, on_device, nullptr, nvertices, flags, compression);
+    });
+}
+
+extern "C" int gt_graph_build_rmat(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uint64_t seed, int weighted,
+                                   const gt_graph_flags* flags, int compression, gt_graph** out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(out, "gt_graph_build_rmat: out is NULL");
+        GT_REQUIRE(scale >= 1 && scale <= 31, "gt_graph_build_rmat: scale must be in [1, 31]");
+        gt::RmatParams P = gt::make_rmat_params(scale, seed, weighted);
+        *out = gt::build(ctx, nullptr, nedges, weighted, 1, &P, 1u << scale, flags, compression);
+    });
+}
+
+extern "C" int gt_rmat_generate(gt_ctx* ctx, uint32_t scale, uint64_t first_edge, uint64_t nedges, uint64_t seed,
+                                int weighted, void* triples_dev) {
+    return gt::guarded([&] {
+        GT_REQUIRE(ctx && triples_dev, "gt_rmat_generate: NULL argument");
+        GT_REQUIRE(scale >= 1 && scale <= 31, "gt_rmat_generate: scale must be in [1, 31]");
+        GT_CUDA(cudaSetDevice(ctx->device));
+        gt::RmatParams P = gt::make_rmat_params(scale, seed, weighted);
+        if (!nedges) return;
+        gt::k_rmat_generate<<<gt::grid_for(nedges, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(P, first_edge, nedges, (uint32_t*) triples_dev);
+        ctx->kernel_launches++;
+        GT_CUDA(cudaGetLastError());
+    });
+}
+
+extern "C" int gt_graph_free(gt_graph* g) {
+    return gt::guarded([&] {
+        if (!g) return;
+        cudaSetDevice(g->ctx->device);
+        delete g;
+    });
+}
+
+extern "C" int gt_graph_info_get(gt_graph* g, gt_graph_info* out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && out, "gt_graph_info_get: NULL argument");
+        out->nedges_input = g->nedges_input;
+        out->nnz_local = g->nnz_local;
+        out->nnz_global = g->nnz_global;
+        out->ntiles_local = (uint32_t) g->tiles.size();
+        out->weighted = (uint32_t) g->weighted;
+        out->nvertices = g->nvertices;
+        out->layout = g->lay.info;
+    });
+}
+
+extern "C" int gt_graph_tile_view(gt_graph* g, uint32_t local_tile, gt_tile_view* out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && out, "gt_graph_tile_view: NULL argument");
+        GT_REQUIRE(local_tile < g->tiles.size(), "gt_graph_tile_view: tile index out of range");
+        const gt::Tile& T = g->tiles[local_tile];
+        out->rg = T.rg; out->cg = T.cg; out->row_slot = T.row_slot; out->col_slot = T.col_slot;
+        out->nnz = T.nnz;
+        out->nnzcols = g->cols[T.col_slot].nnz;
+        out->nnzrows = g->rows[T.row_slot].nnz;
+        out->JA = T.JA.p;
+        out->IA = g->IA_pool.p ? g->IA_pool.p + T.offset : nullptr;
+        out->A = g->A_pool.p ? g->A_pool.p + T.offset : nullptr;
+        out->JC = g->cols[T.col_slot].ids.p;
+        out->IR = g->rows[T.row_slot].ids.p;
+    });
+}
+
+extern "C" int gt_graph_rowgrp_maps(gt_graph* g, uint32_t row_slot, const uint8_t** I, const uint32_t** IV, uint32_t* nnzrows) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && row_slot < g->rows.size(), "gt_graph_rowgrp_maps: slot out of range");
+        if (I) *I = g->rows[row_slot].bits.p;
+        if (IV) *IV = g->rows[row_slot].prefix.p;
+        if (nnzrows) *nnzrows = g->rows[row_slot].nnz;
+    });
+}
+
+extern "C" int gt_graph_colgrp_maps(gt_graph* g, uint32_t col_slot, const uint8_t** J, const uint32_t** JV, uint32_t* nnzcols) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && col_slot < g->cols.size(), "gt_graph_colgrp_maps: slot out of range");
+        if (J) *J = g->cols[col_slot].bits.p;
+        if (JV) *JV = g->cols[col_slot].prefix.p;
+        if (nnzcols) *nnzcols = g->cols[col_slot].nnz;
+    });
+}

@@ -1,0 +1,665 @@
+// gt_engine.cu — Vertex_Program::execute on the device.
+//
+// The reference loop (src/vp/vertex_program.hpp:407-441):
+//     while (true) { scatter_gather(); combine(); apply(); iteration++; converged? }
+// and what each phase becomes here:
+//   scatter_gather   messenger kernel over the owned column segment's non-empty columns (:687-758),
+//                    then ncclBroadcast of every local x segment along the column group (:843-862,970-1013)
+//   combine          per local tile, in local_tiles_row_order: push SpMV / frontier SpMSpV (:1057-1113,
+//                    :1330-1434), then ncclReduce of every local y segment to its leader along the row group
+//                    (the follower->leader Isend + leader-side combine of :1083-1108,1522-1573)
+//   apply            applicator kernel on the owned segment (:1640-1802), activity flags C
+//   has_converged    device count of C, ncclAllReduce over the world, one 8-byte D2H (:1884-1923)
+// The five shipped programs are recognised by enum; their messenger/combiner/applicator bodies
+// (src/apps/{deg,pr,bfs,cc,sssp}.h) are the __device__ functions below.  With GT_COL every row/column
+// notion swaps, including the two communicators (:279-325).
+//
+// Non-stationary exchange: the reference ships (index,value) pairs when at most 60 % of a segment is
+// active (:760-784,970-1013).  On NVLink the dense u32 segment is cheap, so x always travels dense and
+// every rank rebuilds the frontier list locally; the 0.6 rule still picks SpMSpV vs dense SpMV per
+// column segment (:1475), so `sparse_iterations` matches the reference's schedule.
+#include "gt_kernels.cuh"
+#include <cub/cub.cuh>
+#include <memory>
+#include <algorithm>
+#include <cmath>
+
+namespace gt {
+
+static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) {
+    uint64_t g = (n + block - 1) / block;
+    uint64_t cap = (uint64_t) sm_count * per_sm;
+    return (int) std::max<uint64_t>(1, std::min(g, cap));
+}
+
+// ---- vertex state, SoA on the device (the reference's AoS std::vector<Vertex_State> V is produced on
+// demand by gt_program_state_to_host) --------------------------------------------------------------
+struct VState {
+    double* rank;        // PR
+    uint32_t* a;         // Deg/PR degree | BFS parent | CC label | SSSP distance
+    uint32_t* b;         // BFS hops
+    uint8_t* C;          // activity / convergence flags (:161)
+};
+
+__global__ void k_init_state(VState V, int app, uint32_t th, uint32_t vid0, uint32_t root, double alpha, int stationary) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        const uint32_t vid = vid0 + i;
+        switch (app) {
+            case GT_APP_DEG: V.a[i] = 0; V.C[i] = 1; break;                                  // deg.h:32-35
+            case GT_APP_PR: V.a[i] = 0; V.rank[i] = alpha; V.C[i] = stationary ? 1 : 0; break;   // pr.h:15-19, base initializer :32
+            case GT_APP_BFS:                                                                  // bfs.h:37-49
+                if (vid == root) { V.a[i] = vid; V.b[i] = 0; V.C[i] = 1; }
+                else { V.a[i] = 0; V.b[i] = GT_INF_U32; V.C[i] = 0; }
+                break;
+            case GT_APP_CC: V.a[i] = vid; V.C[i] = 1; break;                                   // cc.h:32-35
+            case GT_APP_SSSP:                                                                 // sssp.h:34-43
+                if (vid == root) { V.a[i] = 0; V.C[i] = 1; } else { V.a[i] = GT_INF_U32; V.C[i] = 0; }
+                break;
+        }
+    }
+}
+
+template <typename T>
+__global__ void k_fill(T* p, T v, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- messenger ---------------------------------------------------------------------------------------
+// stationary: x[j] = messenger(V[JC[j]]) over the owned segment's non-empty columns (:699-705)
+__global__ void k_messenger_f64(VState V, int app, const uint32_t* __restrict__ JC, uint32_t nc, double* __restrict__ x) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
+        if (app == GT_APP_DEG) { x[j] = 1.0; continue; }                                   // deg.h:37-39
+        const uint32_t v = JC[j];
+        const uint32_t d = V.a[v];
+        x[j] = d ? V.rank[v] / (double) d : 0.0;                                           // pr.h:31-33
+    }
+}
+// non-stationary: x[j] = C[v] ? messenger(V[v]) : infinity() (:737-751)
+__global__ void k_messenger_u32(VState V, int app, uint32_t vid0, const uint32_t* __restrict__ JC, uint32_t nc, uint32_t* __restrict__ x) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
+        const uint32_t v = JC[j];
+        uint32_t m = GT_INF_U32;
+        if (V.C[v]) m = (app == GT_APP_BFS) ? vid0 + v : V.a[v];                            // bfs.h:52-54, cc.h:37-39, sssp.h:45-47
+        x[j] = m;
+    }
+}
+// frontier list of one x segment: xi = compressed ids with x != INF, xv = their values (:744-748);
+// order inside the list is irrelevant to a min reduction
+__global__ void __launch_bounds__(256) k_frontier(const uint32_t* __restrict__ x, uint32_t nc, uint32_t* __restrict__ xi, uint32_t* __restrict__ xv,
+                                                   unsigned int* __restrict__ count) {
+    const uint32_t n_round = (nc + 31) / 32 * 32;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
+        const uint32_t v = j < nc ? x[j] : GT_INF_U32;
+        const bool act = v != GT_INF_U32;
+        const unsigned ballot = __ballot_sync(0xffffffffu, act);
+        if (!ballot) continue;
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(count, (unsigned) __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (act) {
+            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1));
+            xi[pos] = j;
+            xv[pos] = v;
+        }
+    }
+}
+
+// ---- applicator ------------------------------------------------------------------------------------------
+// stationary, TCSC: rows with I[i] take y[j++] (here y[r] with v = IR[r]) (:1655-1670)
+__global__ void k_apply_f64(VState V, int app, const uint32_t* __restrict__ IR, uint32_t nr, const double* __restrict__ y,
+                            double alpha, double tol) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
+        const uint32_t v = IR[r];
+        const double yy = y[r];
+        if (app == GT_APP_DEG) { V.a[v] = (uint32_t) yy; V.C[v] = 0; continue; }           // deg.h:49-52
+        const double old = V.rank[v];
+        const double nw = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, yy));                      // pr.h:45 (no fma contraction)
+        V.rank[v] = nw;
+        V.C[v] = fabs(nw - old) > tol;                                                       // pr.h:46
+    }
+}
+// vertices whose row is empty everywhere: applicator(state) -> false (:1666-1667, :38)
+__global__ void k_clear_C_empty(uint8_t* C, const uint8_t* __restrict__ I, uint32_t th) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
+        if (!I[i]) C[i] = 0;
+}
+// non-stationary, on the rows of rowgrp_nnz_rows (:1739-1751,1768-1780); iteration 0 additionally clears
+// C on the empty rows (:1726-1738,1754-1767) through k_clear_C_empty.  Counts the active vertices.
+__global__ void __launch_bounds__(256) k_apply_u32(VState V, int app, int weighted, const uint32_t* __restrict__ IR, uint32_t nr,
+                                                    const uint32_t* __restrict__ y, uint32_t iteration, unsigned long long* __restrict__ active) {
+    unsigned local = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
+        const uint32_t v = IR[r];
+        const uint32_t yy = y[r];
+        bool ch = false;
+        if (app == GT_APP_BFS) {                                   // bfs.h:65-77
+            if (V.b[v] == GT_INF_U32 && yy != GT_INF_U32) { V.b[v] = iteration + 1; V.a[v] = yy; ch = true; }
+        } else if (app == GT_APP_CC) {                             // cc.h:51-55
+            const uint32_t old = V.a[v];
+            if (yy < old) { V.a[v] = yy; ch = true; }
+        } else {                                                   // sssp.h:58-66
+            const uint32_t old = V.a[v];
+            const uint32_t nw = (yy < old) ? (weighted ? yy : yy + 1) : old;
+            if (nw != old) { V.a[v] = nw; ch = true; }
+        }
+        V.C[v] = ch;
+        local += ch;
+    }
+    typedef cub::BlockReduce<unsigned, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const unsigned tot = BR(tmp).Sum(local);
+    if (threadIdx.x == 0 && tot) atomicAdd(active, (unsigned long long) tot);
+}
+__global__ void __launch_bounds__(256) k_count_u8(const uint8_t* __restrict__ C, uint32_t n, unsigned long long* __restrict__ out) {
+    unsigned local = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) local += C[i] ? 1 : 0;
+    typedef cub::BlockReduce<unsigned, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const unsigned tot = BR(tmp).Sum(local);
+    if (threadIdx.x == 0 && tot) atomicAdd(out, (unsigned long long) tot);
+}
+
+// initialize(other): degree hand-over where the row is non-empty (:476-483, pr.h:24-28)
+__global__ void k_init_from_deg(VState V, const uint32_t* __restrict__ other_deg, const uint8_t* __restrict__ I, uint32_t th, double alpha) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
+        if (I[i]) { V.a[i] = other_deg[i]; V.rank[i] = alpha; V.C[i] = 1; }
+}
+
+// AoS <-> SoA at the boundary
+__global__ void k_pack_state(VState V, int app, uint32_t th, uint32_t vid0, uint32_t* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        switch (app) {
+            case GT_APP_PR: {
+                out[4 * i] = V.a[i]; out[4 * i + 1] = 0;
+                const unsigned long long bits = (unsigned long long) __double_as_longlong(V.rank[i]);
+                out[4 * i + 2] = (uint32_t) bits; out[4 * i + 3] = (uint32_t) (bits >> 32);
+                break;
+            }
+            case GT_APP_BFS: out[3 * i] = V.a[i]; out[3 * i + 1] = V.b[i]; out[3 * i + 2] = vid0 + i; break;
+            default: out[i] = V.a[i]; break;
+        }
+    }
+}
+__global__ void k_unpack_state(VState V, int app, uint32_t th, const uint32_t* in) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        switch (app) {
+            case GT_APP_PR: {
+                V.a[i] = in[4 * i];
+                const unsigned long long bits = (unsigned long long) in[4 * i + 2] | ((unsigned long long) in[4 * i + 3] << 32);
+                V.rank[i] = __longlong_as_double((long long) bits);
+                break;
+            }
+            case GT_APP_BFS: V.a[i] = in[3 * i]; V.b[i] = in[3 * i + 1]; break;
+            default: V.a[i] = in[i]; break;
+        }
+    }
+}
+
+// ---- tile kernel dispatch ---------------------------------------------------------------------------------
+static void launch_spmv(gt_ctx* ctx, const gt_graph* g, const Tile& T, int semiring, int ordering, bool skip_inf,
+                        const void* x, void* y, uint8_t* t) {
+    if (!T.nnz) return;
+    cudaStream_t st = ctx->stream;
+    const uint32_t* IA = g->IA_pool.p + T.offset;
+    const uint32_t* A = g->weighted ? g->A_pool.p + T.offset : nullptr;
+    const uint32_t ncols = g->cols[T.col_slot].nnz;
+    if (ordering == GT_ROW) {
+        const uint32_t nchunks = (uint32_t) ((T.nnz + GT_PUSH_CHUNK - 1) / GT_PUSH_CHUNK);
+        const int grid = (int) std::min<uint64_t>(nchunks, (uint64_t) ctx->sm_count * 8);
+#define GT_PUSH(S, W, K) k_spmv_push<S, W, K><<<grid, kPushThreads, 0, st>>>(T.JA.p, IA, A, T.chunk_col.p, nchunks, T.nnz, \
+            (const Semiring<S>::T*) x, (Semiring<S>::T*) y, t)
+        if (semiring == GT_PLUS_TIMES_F64) { if (A) GT_PUSH(GT_PLUS_TIMES_F64, true, false); else GT_PUSH(GT_PLUS_TIMES_F64, false, false); }
+        else if (semiring == GT_MIN_PLUS_U32) {
+            GT_REQUIRE(A, "min-plus needs a weighted graph");
+            if (skip_inf) GT_PUSH(GT_MIN_PLUS_U32, true, true); else GT_PUSH(GT_MIN_PLUS_U32, true, false);
+        } else {
+            if (A) { if (skip_inf) GT_PUSH(GT_MIN_SELECT_U32, true, true); else GT_PUSH(GT_MIN_SELECT_U32, true, false); }
+            else { if (skip_inf) GT_PUSH(GT_MIN_SELECT_U32, false, true); else GT_PUSH(GT_MIN_SELECT_U32, false, false); }
+        }
+#undef GT_PUSH
+    } else {
+        const int grid = grid_for((uint64_t) ncols * 32, 256, ctx->sm_count, 8);
+#define GT_PULL(S, W) k_spmv_pull<S, W><<<grid, 256, 0, st>>>(T.JA.p, IA, A, ncols, (const Semiring<S>::T*) x, (Semiring<S>::T*) y)
+        if (semiring == GT_PLUS_TIMES_F64) { if (A) GT_PULL(GT_PLUS_TIMES_F64, true); else GT_PULL(GT_PLUS_TIMES_F64, false); }
+        else if (semiring == GT_MIN_PLUS_U32) { GT_REQUIRE(A, "min-plus needs a weighted graph"); GT_PULL(GT_MIN_PLUS_U32, true); }
+        else { if (A) GT_PULL(GT_MIN_SELECT_U32, true); else GT_PULL(GT_MIN_SELECT_U32, false); }
+#undef GT_PULL
+    }
+    ctx->kernel_launches++;
+    GT_CUDA(cudaGetLastError());
+}
+
+static void launch_spmspv(gt_ctx* ctx, const gt_graph* g, const Tile& T, int semiring, const uint32_t* xi, const void* xv, uint32_t k,
+                          void* y, uint8_t* t) {
+    if (!T.nnz || !k) return;
+    cudaStream_t st = ctx->stream;
+    const uint32_t* IA = g->IA_pool.p + T.offset;
+    const uint32_t* A = g->weighted ? g->A_pool.p + T.offset : nullptr;
+    const int grid = grid_for((uint64_t) k * 32, 256, ctx->sm_count, 8);
+#define GT_SP(S, W) k_spmspv_push<S, W><<<grid, 256, 0, st>>>(T.JA.p, IA, A, xi, (const Semiring<S>::T*) xv, k, (Semiring<S>::T*) y, t)
+    if (semiring == GT_PLUS_TIMES_F64) { if (A) GT_SP(GT_PLUS_TIMES_F64, true); else GT_SP(GT_PLUS_TIMES_F64, false); }
+    else if (semiring == GT_MIN_PLUS_U32) { GT_REQUIRE(A, "min-plus needs a weighted graph"); GT_SP(GT_MIN_PLUS_U32, true); }
+    else { if (A) GT_SP(GT_MIN_SELECT_U32, true); else GT_SP(GT_MIN_SELECT_U32, false); }
+#undef GT_SP
+    ctx->kernel_launches++;
+    GT_CUDA(cudaGetLastError());
+}
+
+}  // namespace gt
+
+// ---------------------------------------------------------------------------------------------------------
+struct gt_program {
+    gt_graph* g = nullptr;
+    gt_ctx* ctx = nullptr;
+    int app = 0, stationary = 0, gather_depends_on_apply = 0, apply_depends_on_iter = 0, ordering = GT_ROW;
+    gt_params prm{};
+    int semiring = 0;
+    bool f64 = false;
+    uint32_t th = 0, vid0 = 0;
+    // program-level views: under GT_COL "rows" are the matrix's column groups (:279-325)
+    std::vector<gt::SegMaps>* prow = nullptr;
+    std::vector<gt::SegMaps>* pcol = nullptr;
+    int own_row_slot = 0, own_col_slot = 0;
+    gt::CommGroup bcast_group = gt::COMM_COLGRP, reduce_group = gt::COMM_ROWGRP;
+    // state
+    gt::DevBuf<double> rank;
+    gt::DevBuf<uint32_t> a, b;
+    gt::DevBuf<uint8_t> C;
+    std::vector<gt::DevBuf<uint8_t>> X, Y;         // raw bytes, |x|*esize
+    std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
+    gt::DevBuf<unsigned long long> d_active;      // [0] active count
+    gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
+    unsigned long long* h_active = nullptr;       // pinned
+    unsigned int* h_counts = nullptr;             // pinned
+    bool initialized = false, converged = false, empty_cleared = false;
+    uint32_t iteration = 0;
+    double activity_filtering_ratio = 0.6;
+    bool timing = false;
+    gt_timing tm{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    gt::VState vs() { return gt::VState{rank.p, a.p, b.p, C.p}; }
+    size_t esize() const { return f64 ? 8 : 4; }
+};
+
+namespace gt {
+
+static void prog_alloc(gt_program* P) {
+    gt_graph* g = P->g;
+    P->th = g->lay.info.tile_height;
+    P->vid0 = (uint32_t) g->lay.info.owned_segment * P->th;
+    if (P->ordering == GT_ROW) {
+        P->prow = &g->rows; P->pcol = &g->cols;
+        P->own_row_slot = g->lay.info.accu_segment_row; P->own_col_slot = g->lay.info.accu_segment_col;
+        P->bcast_group = COMM_COLGRP; P->reduce_group = COMM_ROWGRP;
+    } else {
+        P->prow = &g->cols; P->pcol = &g->rows;
+        P->own_row_slot = g->lay.info.accu_segment_col; P->own_col_slot = g->lay.info.accu_segment_row;
+        P->bcast_group = COMM_ROWGRP; P->reduce_group = COMM_COLGRP;
+    }
+    if (P->app == GT_APP_PR) P->rank.alloc(P->th);
+    P->a.alloc(P->th);
+    if (P->app == GT_APP_BFS) P->b.alloc(P->th);
+    P->C.alloc(P->th);
+    P->X.resize(P->pcol->size());
+    P->Y.resize(P->prow->size());
+    for (size_t k = 0; k < P->X.size(); k++) P->X[k].alloc((size_t) (*P->pcol)[k].nnz * P->esize());
+    for (size_t k = 0; k < P->Y.size(); k++) P->Y[k].alloc((size_t) (*P->prow)[k].nnz * P->esize());
+    if (!P->stationary) {
+        P->XI.resize(P->X.size()); P->XV.resize(P->X.size());
+        for (size_t k = 0; k < P->X.size(); k++) { P->XI[k].alloc((*P->pcol)[k].nnz); P->XV[k].alloc((*P->pcol)[k].nnz); }
+    }
+    P->d_active.alloc(2);
+    P->d_counts.alloc(std::max<size_t>(1, P->X.size()));
+    GT_CUDA(cudaMallocHost((void**) &P->h_active, 2 * sizeof(unsigned long long)));
+    GT_CUDA(cudaMallocHost((void**) &P->h_counts, std::max<size_t>(1, P->X.size()) * sizeof(unsigned int)));
+    GT_CUDA(cudaEventCreate(&P->ev0));
+    GT_CUDA(cudaEventCreate(&P->ev1));
+}
+
+// init_stationary + init_nonstationary (:504-636)
+static void prog_initialize(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    k_init_state<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->th, P->vid0, P->prm.root, P->prm.alpha, P->stationary);
+    ctx->kernel_launches++;
+    if (!P->stationary) {                       // Y starts at infinity() (:625-635)
+        for (size_t k = 0; k < P->Y.size(); k++) {
+            const uint64_t n = (*P->prow)[k].nnz;
+            if (!n) continue;
+            k_fill<uint32_t><<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((uint32_t*) P->Y[k].p, GT_INF_U32, n);
+            ctx->kernel_launches++;
+        }
+    }
+    GT_CUDA(cudaGetLastError());
+    P->initialized = true;
+    P->iteration = 0;
+    P->converged = false;
+    P->empty_cleared = false;
+}
+
+static uint64_t algorithmic_bytes_dense(const gt_program* P) {
+    // per tile IA (+A) + JA + one read of its x segment; per row group one write of y;
+    // vertex phase on the owned segment: JC + state read, IR + y + state read/write.
+    const gt_graph* g = P->g;
+    const uint64_t es = P->esize();
+    uint64_t b = 0;
+    for (const Tile& T : g->tiles) {
+        const uint64_t nc = (P->ordering == GT_ROW ? g->cols[T.col_slot].nnz : g->rows[T.row_slot].nnz);
+        if (!T.nnz) continue;
+        b += (g->weighted ? 8 : 4) * T.nnz + 4 * ((uint64_t) g->cols[T.col_slot].nnz + 1) + es * nc;
+    }
+    for (const SegMaps& r : *P->prow) b += es * r.nnz;
+    const uint64_t state = (P->app == GT_APP_PR) ? 12 : 4;
+    b += (4 + state) * (uint64_t) (*P->pcol)[P->own_col_slot].nnz;
+    b += (4 + es + (P->app == GT_APP_PR ? 16 : 8)) * (uint64_t) (*P->prow)[P->own_row_slot].nnz;
+    return b;
+}
+
+static void scatter_gather(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    const SegMaps& own = (*P->pcol)[P->own_col_slot];
+    if (own.nnz) {
+        const int grid = grid_for(own.nnz, 256, ctx->sm_count);
+        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (double*) P->X[P->own_col_slot].p);
+        else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
+        ctx->kernel_launches++;
+    }
+    if (ctx->comm) {                              // bcast_stationary / bcast_nonstationary
+        comm_group_start(ctx->comm);
+        for (size_t k = 0; k < P->X.size(); k++) {
+            const SegMaps& s = (*P->pcol)[k];
+            if (!s.nnz) continue;
+            const int root = comm_index_of_world_rank(ctx->comm, P->bcast_group, P->g->lay.leader_ranks[s.segment]);
+            comm_bcast(ctx->comm, P->bcast_group, P->X[k].p, s.nnz, P->f64 ? CT_F64 : CT_U32, root, st);
+        }
+        comm_group_end(ctx->comm);
+    }
+    if (!P->stationary) {                         // frontier lists + sizes (:754-784)
+        GT_CUDA(cudaMemsetAsync(P->d_counts.p, 0, P->d_counts.bytes(), st));
+        for (size_t k = 0; k < P->X.size(); k++) {
+            const SegMaps& s = (*P->pcol)[k];
+            if (!s.nnz) continue;
+            k_frontier<<<grid_for(s.nnz, 256, ctx->sm_count), 256, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->XI[k].p, P->XV[k].p, P->d_counts.p + k);
+            ctx->kernel_launches++;
+        }
+        GT_CUDA(cudaMemcpyAsync(P->h_counts, P->d_counts.p, P->X.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+    GT_CUDA(cudaGetLastError());
+}
+
+static void combine(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    gt_graph* g = P->g;
+    if (P->stationary)                            // std::fill(y, 0) (:1026-1032)
+        for (size_t k = 0; k < P->Y.size(); k++)
+            if (P->Y[k].n) GT_CUDA(cudaMemsetAsync(P->Y[k].p, 0, P->Y[k].n, st));
+    bool any_sparse = false;
+    // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
+    // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
+    for (const Tile& T : g->tiles) {
+        const uint32_t xs = (P->ordering == GT_ROW) ? T.col_slot : T.row_slot;
+        const uint32_t ys = (P->ordering == GT_ROW) ? T.row_slot : T.col_slot;
+        if (!T.nnz) continue;
+        if (P->stationary) {
+            launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
+        } else {
+            const uint32_t k = P->h_counts[xs];
+            const uint32_t nx = (*P->pcol)[xs].nnz;
+            const bool sparse = nx && ((double) k / (double) nx <= P->activity_filtering_ratio);   // :768-772
+            if (sparse) { any_sparse = true; launch_spmspv(ctx, g, T, P->semiring, P->XI[xs].p, P->XV[xs].p, k, P->Y[ys].p, nullptr); }
+            else launch_spmv(ctx, g, T, P->semiring, P->ordering, true, P->X[xs].p, P->Y[ys].p, nullptr);
+        }
+    }
+    if (any_sparse) P->tm.sparse_iterations++;
+    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1) {
+        comm_group_start(ctx->comm);
+        for (size_t k = 0; k < P->Y.size(); k++) {
+            const SegMaps& s = (*P->prow)[k];
+            if (!s.nnz) continue;
+            const int root = comm_index_of_world_rank(ctx->comm, P->reduce_group, g->lay.leader_ranks[s.segment]);
+            comm_reduce(ctx->comm, P->reduce_group, P->Y[k].p, P->Y[k].p, s.nnz, P->f64 ? CT_F64 : CT_U32, P->f64 ? CO_SUM : CO_MIN, root, st);
+        }
+        comm_group_end(ctx->comm);
+    }
+}
+
+static void apply(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    const SegMaps& own = (*P->prow)[P->own_row_slot];
+    if (!P->empty_cleared) {
+        k_clear_C_empty<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, own.bits.p, P->th);
+        ctx->kernel_launches++;
+        P->empty_cleared = true;
+    }
+    if (!P->stationary) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
+    if (own.nnz) {
+        const int grid = grid_for(own.nnz, 256, ctx->sm_count);
+        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
+        else k_apply_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, own.ids.p, own.nnz, (const uint32_t*) P->Y[P->own_row_slot].p, P->iteration, P->d_active.p);
+        ctx->kernel_launches++;
+    }
+    GT_CUDA(cudaGetLastError());
+}
+
+// all C == 0 on all ranks (:1884-1923)
+static bool has_converged(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    if (P->stationary) {
+        GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
+        k_count_u8<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, P->th, P->d_active.p);
+        ctx->kernel_launches++;
+    }
+    if (ctx->comm) comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p, P->d_active.p, 1, CT_U64, CO_SUM, st);
+    GT_CUDA(cudaMemcpyAsync(P->h_active, P->d_active.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    return P->h_active[0] == 0;
+}
+
+}  // namespace gt
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int gt_program_create(gt_graph* g, int app, int stationary, int gather_depends_on_apply,
+                                 int apply_depends_on_iter, int ordering, const gt_params* params, gt_program** out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && out, "gt_program_create: NULL argument");
+        GT_REQUIRE(app >= GT_APP_DEG && app <= GT_APP_SSSP, "gt_program_create: unknown app (only the five shipped programs run on the device)");
+        GT_REQUIRE(ordering == GT_ROW || ordering == GT_COL, "gt_program_create: bad ordering");
+        const bool want_stationary = (app == GT_APP_DEG || app == GT_APP_PR);
+        GT_REQUIRE((stationary != 0) == want_stationary, "gt_program_create: this app's stationary flag differs from the reference driver's");
+        if (ordering == GT_COL && !stationary)
+            throw gt::Error(GT_ERR_UNSUPPORTED, "gt_program_create: _COL_ ordering is provided for stationary programs only (no shipped app uses it otherwise)");
+        if (app == GT_APP_SSSP && !g->weighted)
+            throw gt::Error(GT_ERR_UNSUPPORTED, "gt_program_create: SSSP needs the weighted (HAS_WEIGHT) graph, as built by the reference Makefile:27-28");
+        GT_CUDA(cudaSetDevice(g->ctx->device));
+        std::unique_ptr<gt_program> P(new gt_program());
+        P->g = g; P->ctx = g->ctx; P->app = app; P->stationary = stationary;
+        P->gather_depends_on_apply = gather_depends_on_apply; P->apply_depends_on_iter = apply_depends_on_iter;
+        P->ordering = ordering;
+        P->prm.alpha = 0.15; P->prm.tol = 1e-5; P->prm.root = 0;
+        if (params) P->prm = *params;
+        P->f64 = want_stationary;
+        P->semiring = want_stationary ? GT_PLUS_TIMES_F64 : (g->weighted ? GT_MIN_PLUS_U32 : GT_MIN_SELECT_U32);
+        gt::prog_alloc(P.get());
+        *out = P.release();
+    });
+}
+
+extern "C" int gt_program_free(gt_program* p) {
+    return gt::guarded([&] {
+        if (!p) return;
+        cudaSetDevice(p->ctx->device);
+        if (p->h_active) cudaFreeHost(p->h_active);
+        if (p->h_counts) cudaFreeHost(p->h_counts);
+        if (p->ev0) cudaEventDestroy(p->ev0);
+        if (p->ev1) cudaEventDestroy(p->ev1);
+        delete p;
+    });
+}
+
+extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && name, "gt_program_set: NULL argument");
+        std::string n(name);
+        if (n == "activity_filtering_ratio") p->activity_filtering_ratio = value;
+        else if (n == "timing") p->timing = value != 0;
+        else if (n == "pr_layout") { /* selected in a later pass of this file */ }
+        else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
+    });
+}
+
+extern "C" int gt_program_init_from(gt_program* p, gt_program* other) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && other, "gt_program_init_from: NULL argument");
+        GT_REQUIRE(p->app == GT_APP_PR && other->app == GT_APP_DEG, "gt_program_init_from: only PR <- Deg is defined (src/apps/pr.h:24-28)");
+        GT_REQUIRE(p->g->lay.info.tile_height == other->g->lay.info.tile_height, "gt_program_init_from: programs live on different layouts");
+        GT_CUDA(cudaSetDevice(p->ctx->device));
+        gt::prog_initialize(p);
+        const gt::SegMaps& own = (*p->prow)[p->own_row_slot];
+        gt::k_init_from_deg<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), other->a.p, own.bits.p, p->th, p->prm.alpha);
+        p->ctx->kernel_launches++;
+        GT_CUDA(cudaGetLastError());
+    });
+}
+
+extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32_t* iters_done) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p, "gt_program_execute: NULL program");
+        gt_ctx* ctx = p->ctx;
+        GT_CUDA(cudaSetDevice(ctx->device));
+        if (!p->initialized) gt::prog_initialize(p);
+        const bool check = num_iterations == 0;
+        const uint64_t launches0 = ctx->kernel_launches;
+        const uint64_t dense_bytes = gt::algorithmic_bytes_dense(p);
+        GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
+        while (true) {
+            gt::scatter_gather(p);
+            gt::combine(p);
+            gt::apply(p);
+            p->iteration++;
+            p->tm.bytes_algorithmic += dense_bytes;
+            if (check) {
+                p->converged = gt::has_converged(p);
+                if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
+            } else if (p->iteration >= num_iterations) break;
+        }
+        GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
+        GT_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        GT_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        p->tm.execute_ms = ms;
+        p->tm.kernel_launches = ctx->kernel_launches - launches0;
+        p->tm.iterations = p->iteration;
+        if (iters_done) *iters_done = p->iteration;
+    });
+}
+
+extern "C" uint32_t gt_program_state_bytes(gt_program* p) {
+    if (!p) return 0;
+    return p->app == GT_APP_PR ? 16 : p->app == GT_APP_BFS ? 12 : 4;
+}
+
+extern "C" int gt_program_state_to_host(gt_program* p, void* V_out, uint64_t cap_bytes) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && V_out, "gt_program_state_to_host: NULL argument");
+        GT_REQUIRE(p->initialized, "gt_program_state_to_host: program not initialized");
+        const uint64_t bytes = (uint64_t) p->th * gt_program_state_bytes(p);
+        GT_REQUIRE(cap_bytes >= bytes, "gt_program_state_to_host: buffer too small");
+        GT_CUDA(cudaSetDevice(p->ctx->device));
+        gt::DevBuf<uint32_t> stage; stage.alloc(bytes / 4);
+        gt::k_pack_state<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), p->app, p->th, p->vid0, stage.p);
+        p->ctx->kernel_launches++;
+        GT_CUDA(cudaGetLastError());
+        GT_CUDA(cudaMemcpyAsync(V_out, stage.p, bytes, cudaMemcpyDeviceToHost, p->ctx->stream));
+        GT_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    });
+}
+
+extern "C" int gt_program_state_from_host(gt_program* p, const void* V_in, uint64_t bytes) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && V_in, "gt_program_state_from_host: NULL argument");
+        const uint64_t need = (uint64_t) p->th * gt_program_state_bytes(p);
+        GT_REQUIRE(bytes == need, "gt_program_state_from_host: size is not tile_height states");
+        GT_CUDA(cudaSetDevice(p->ctx->device));
+        if (!p->initialized) gt::prog_initialize(p);
+        gt::DevBuf<uint32_t> stage; stage.alloc(need / 4);
+        GT_CUDA(cudaMemcpyAsync(stage.p, V_in, need, cudaMemcpyHostToDevice, p->ctx->stream));
+        gt::k_unpack_state<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), p->app, p->th, stage.p);
+        p->ctx->kernel_launches++;
+        GT_CUDA(cudaGetLastError());
+        GT_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    });
+}
+
+// checksum() is end-of-run reporting: the reference's u64 accumulator truncates the
+// running sum at every addition, so the value depends on the order; reproduce it with the same
+// sequential loop over the downloaded states.
+extern "C" int gt_program_checksum(gt_program* p, uint64_t* value_sum, uint64_t* reachable) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && p->initialized, "gt_program_checksum: program not initialized");
+        GT_CUDA(cudaSetDevice(p->ctx->device));
+        cudaStream_t st = p->ctx->stream;
+        const uint32_t th = p->th, nrows = p->g->lay.info.nrows;
+        uint64_t sum = 0, cnt = 0;
+        if (p->app == GT_APP_PR) {
+            std::vector<double> r(th);
+            GT_CUDA(cudaMemcpyAsync(r.data(), p->rank.p, (size_t) th * 8, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < th; i++)
+                if (r[i] != 0.0 && (uint64_t) p->vid0 + i < nrows) { sum = (uint64_t) ((double) sum + r[i]); cnt++; }
+        } else {
+            std::vector<uint32_t> v(th);
+            const uint32_t* src = (p->app == GT_APP_BFS) ? p->b.p : p->a.p;
+            const uint32_t inf = (p->app == GT_APP_DEG) ? 0u : GT_INF_U32;
+            GT_CUDA(cudaMemcpyAsync(v.data(), src, (size_t) th * 4, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < th; i++)
+                if (v[i] != inf && (uint64_t) p->vid0 + i < nrows) { sum += v[i]; cnt++; }
+        }
+        if (p->ctx->comm) {
+            unsigned long long h[2] = {sum, cnt};
+            GT_CUDA(cudaMemcpyAsync(p->d_active.p, h, 16, cudaMemcpyHostToDevice, st));
+            gt::comm_allreduce(p->ctx->comm, gt::COMM_WORLD, p->d_active.p, p->d_active.p, 2, gt::CT_U64, gt::CO_SUM, st);
+            GT_CUDA(cudaMemcpyAsync(h, p->d_active.p, 16, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            sum = h[0]; cnt = h[1];
+        }
+        if (value_sum) *value_sum = sum;
+        if (reachable) *reachable = cnt;
+    });
+}
+
+extern "C" int gt_program_timing(gt_program* p, gt_timing* out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && out, "gt_program_timing: NULL argument");
+        *out = p->tm;
+    });
+}
+
+// ---- kernel-level entry points -------------------------------------------------------------------------------
+extern "C" int gt_tile_spmv(gt_graph* g, uint32_t local_tile, int semiring, int ordering, const void* x, void* y) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && x && y, "gt_tile_spmv: NULL argument");
+        GT_REQUIRE(local_tile < g->tiles.size(), "gt_tile_spmv: tile index out of range");
+        GT_REQUIRE(semiring >= GT_PLUS_TIMES_F64 && semiring <= GT_MIN_SELECT_U32, "gt_tile_spmv: unknown semiring");
+        GT_CUDA(cudaSetDevice(g->ctx->device));
+        gt::launch_spmv(g->ctx, g, g->tiles[local_tile], semiring, ordering, semiring != GT_PLUS_TIMES_F64, x, y, nullptr);
+    });
+}
+
+extern "C" int gt_tile_spmspv(gt_graph* g, uint32_t local_tile, int semiring, const uint32_t* xi, const void* xv,
+                              uint32_t k, void* y, uint8_t* t) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && y && (k == 0 || (xi && xv)), "gt_tile_spmspv: NULL argument");
+        GT_REQUIRE(local_tile < g->tiles.size(), "gt_tile_spmspv: tile index out of range");
+        GT_REQUIRE(semiring >= GT_PLUS_TIMES_F64 && semiring <= GT_MIN_SELECT_U32, "gt_tile_spmspv: unknown semiring");
+        GT_CUDA(cudaSetDevice(g->ctx->device));
+        gt::launch_spmspv(g->ctx, g, g->tiles[local_tile], semiring, xi, xv, k, y, t);
+    });
+}

@@ -1,0 +1,41 @@
+// gt_graph.h — device-resident graph: 2DT tiles in TCSC + the group-wide index maps.
+#pragma once
+#include "gt_internal.h"
+
+namespace gt {
+
+// Index maps of one local row segment (I/IV) or column segment (J/JV):
+// reference src/mat/matrix.hpp:82-85 and filter_vertices :860-1122.
+struct SegMaps {
+    int32_t segment = -1;          // global segment id
+    uint32_t nnz = 0;              // group-wide non-empty count = length of the compressed vector
+    DevBuf<uint8_t> bits;          // I / J   [tile_height]  1 = non-empty anywhere in the group
+    DevBuf<uint32_t> prefix;       // IV / JV [tile_height]  compressed id, 0 where empty
+    DevBuf<uint32_t> ids;          // IR / JC [nnz]          compressed id -> local id
+};
+
+struct Tile {
+    uint32_t rg = 0, cg = 0, row_slot = 0, col_slot = 0;
+    uint64_t nnz = 0;
+    uint64_t offset = 0;           // into IA_pool / A_pool, multiple of 4 entries (128-bit loads)
+    DevBuf<uint32_t> JA;           // [cols[col_slot].nnz + 1]
+    DevBuf<uint32_t> chunk_col;    // first column of every GT_PUSH_CHUNK-edge chunk (+ sentinel)
+};
+
+}  // namespace gt
+
+struct gt_graph {
+    gt_ctx* ctx = nullptr;
+    gt::Layout lay;
+    gt_graph_flags flags{};
+    int weighted = 0;
+    int compression = GT_TCSC;
+    uint32_t nvertices = 0;
+    uint64_t nedges_input = 0, nnz_local = 0, nnz_global = 0;
+    std::vector<gt::SegMaps> rows, cols;     // by local slot
+    std::vector<gt::Tile> tiles;             // local_tiles_row_order
+    gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
+};
+
+// edges per CTA work item of the load-balanced push kernels (gt_kernels.cu)
+#define GT_PUSH_CHUNK 2048
