@@ -70,6 +70,8 @@ PROTOTYPES = {
     "gt_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gt_ctx_destroy": (C.c_int, [C.c_void_p]),
     "gt_ctx_sync": (C.c_int, [C.c_void_p]),
+    "gt_ctx_timer_begin": (C.c_int, [C.c_void_p]),
+    "gt_ctx_timer_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "gt_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "gt_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "gt_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -99,6 +101,7 @@ PROTOTYPES = {
     "gt_program_state_from_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "gt_program_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gt_program_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "gt_program_run_phase": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_program_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
 }
 

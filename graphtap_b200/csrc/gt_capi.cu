@@ -54,8 +54,29 @@ extern "C" int gt_ctx_destroy(gt_ctx* ctx) {
         cudaSetDevice(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         gt::comm_destroy(ctx->comm);
+        if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
+    });
+}
+
+extern "C" int gt_ctx_timer_begin(gt_ctx* ctx) {
+    return gt::guarded([&] {
+        GT_REQUIRE(ctx, "gt_ctx_timer_begin: NULL ctx");
+        GT_CUDA(cudaSetDevice(ctx->device));
+        if (!ctx->ev0) { GT_CUDA(cudaEventCreate(&ctx->ev0)); GT_CUDA(cudaEventCreate(&ctx->ev1)); }
+        GT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    });
+}
+extern "C" int gt_ctx_timer_end(gt_ctx* ctx, double* elapsed_ms) {
+    return gt::guarded([&] {
+        GT_REQUIRE(ctx && ctx->ev0 && elapsed_ms, "gt_ctx_timer_end: no timer running");
+        GT_CUDA(cudaSetDevice(ctx->device));
+        GT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        GT_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        GT_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        *elapsed_ms = ms;
     });
 }
 

@@ -509,6 +509,7 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         std::string n(name);
         if (n == "activity_filtering_ratio") p->activity_filtering_ratio = value;
         else if (n == "timing") p->timing = value != 0;
+        else if (n == "iteration") { p->iteration = (uint32_t) value; p->converged = false; }   // public member, vertex_program.hpp:60
         else if (n == "pr_layout") { /* selected in a later pass of this file */ }
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
@@ -557,6 +558,17 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         p->tm.kernel_launches = ctx->kernel_launches - launches0;
         p->tm.iterations = p->iteration;
         if (iters_done) *iters_done = p->iteration;
+    });
+}
+
+extern "C" int gt_program_run_phase(gt_program* p, int phase) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && p->initialized, "gt_program_run_phase: program not initialized");
+        GT_REQUIRE(phase >= 0 && phase <= 2, "gt_program_run_phase: phase must be 0, 1 or 2");
+        GT_CUDA(cudaSetDevice(p->ctx->device));
+        if (phase == 0) gt::scatter_gather(p);
+        else if (phase == 1) gt::combine(p);
+        else gt::apply(p);
     });
 }
 

@@ -128,4 +128,5 @@ struct gt_ctx {
     gt::Comm* comm = nullptr;
     int sm_count = 0;
     uint64_t kernel_launches = 0;     // every launch this library makes increments this
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // gt_ctx_timer_*
 };

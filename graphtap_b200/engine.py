@@ -349,3 +349,31 @@ def run_sssp(graph_loader, root=0):
     V.root = root
     V.execute()
     return G, V
+
+
+class DeviceArray:
+    """A raw device buffer (gt_dev_alloc) with numpy upload/download; used by tests and the bench to
+    feed the kernel-level entry points (gt_tile_spmv / gt_tile_spmspv)."""
+
+    def __init__(self, host: np.ndarray | None = None, nbytes: int | None = None):
+        Env.init()
+        self.nbytes = int(host.nbytes if host is not None else nbytes)
+        self.ptr = C.c_void_p()
+        check(lib().gt_dev_alloc(Env.ctx, max(self.nbytes, 1), C.byref(self.ptr)))
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host: np.ndarray):
+        host = np.ascontiguousarray(host)
+        assert host.nbytes <= self.nbytes
+        check(lib().gt_dev_upload(Env.ctx, self.ptr, host.ctypes.data_as(C.c_void_p), host.nbytes))
+
+    def download(self, dtype, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        check(lib().gt_dev_download(Env.ctx, out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            check(lib().gt_dev_free(Env.ctx, self.ptr))
+            self.ptr = None

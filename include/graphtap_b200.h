@@ -72,6 +72,10 @@ typedef struct gt_program gt_program;
 GT_API int gt_nccl_unique_id(void* out128);
 GT_API int gt_ctx_create(int device, int rank, int nranks, const void* nccl_id, gt_ctx** out);
 GT_API int gt_ctx_destroy(gt_ctx* ctx);
+/* CUDA-event stopwatch on the engine stream (the stream every kernel of this library is launched on):
+ * begin records an event, end records another, synchronises and returns the elapsed device time. */
+GT_API int gt_ctx_timer_begin(gt_ctx* ctx);
+GT_API int gt_ctx_timer_end(gt_ctx* ctx, double* elapsed_ms);
 GT_API int gt_ctx_sync(gt_ctx* ctx);                      /* cudaStreamSynchronize on the engine stream */
 GT_API void* gt_ctx_stream(gt_ctx* ctx);                  /* the cudaStream_t every kernel is launched on */
 /* device scratch the caller may use for staging (cudaMalloc / cudaFree / copies on the ctx stream) */
@@ -209,6 +213,10 @@ typedef struct {
     uint32_t sparse_iterations;     /* iterations that ran the frontier SpMSpV                     */
 } gt_timing;
 GT_API int gt_program_timing(gt_program* p, gt_timing* out);
+/* One phase of one iteration in isolation, for per-phase timing (the reference's -DTIMING counters,
+ * src/vp/vertex_program.hpp:640-684,1018-1054,1611-1637): 0 scatter_gather, 1 combine (the SpMV /
+ * SpMSpV over every local tile + the row-group reduce), 2 apply.  Does not advance `iteration`. */
+GT_API int gt_program_run_phase(gt_program* p, int phase);
 /* knobs: name = "activity_filtering_ratio" (default 0.6, :194), "timing" (0/1), "pr_layout"
  * (0 = push over TCSC, 1 = derived pull layout). */
 GT_API int gt_program_set(gt_program* p, const char* name, double value);

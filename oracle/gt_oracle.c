@@ -411,3 +411,36 @@ void gto_checksum_u32(const uint32_t* v, uint64_t n_valid, uint32_t infinity, ui
     for (uint64_t i = 0; i < n_valid; i++) if (v[i] != infinity) { s += v[i]; c++; }
     *sum = s; *count = c;
 }
+
+/* ---- counter-based RMAT stream (host copy of graphtap_b200/rmat.py, used to write CPU-baseline samples) */
+static uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void gto_rmat(uint32_t scale, uint64_t first, uint64_t n, uint64_t seed, int weighted, uint32_t* out) {
+    uint64_t mul[3], add[3];
+    const uint64_t mask = (1ull << scale) - 1;
+    const uint32_t sh = scale / 2 > 1 ? scale / 2 : 1;
+    uint64_t k = splitmix64(seed * 0x632BE59BD9B4E019ull + 0x1234567ull);
+    for (int r = 0; r < 3; r++) { k = splitmix64(k + (uint64_t) r); mul[r] = k | 1ull; add[r] = k >> 17; }
+    const uint64_t base = splitmix64(seed ^ 0xA5A5A5A5A5A5A5A5ull);
+    uint64_t zero = (1ull << (scale / 4 > 1 ? scale / 4 : 1)) - 1;
+    for (int r = 0; r < 3; r++) { zero = (zero * mul[r] + add[r]) & mask; zero ^= zero >> sh; }
+    const int stride = weighted ? 3 : 2;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t ctr = base + (first + i) * 32ull;
+        uint64_t s = 0, d = 0, r = 0;
+        for (uint32_t lvl = 0; lvl < scale; lvl++) {
+            uint32_t u;
+            if ((lvl & 1) == 0) { r = splitmix64(ctr + (lvl >> 1)); u = (uint32_t) r; } else u = (uint32_t) (r >> 32);
+            s = (s << 1) | (u >= 3264175144u);
+            d = (d << 1) | ((u >= 2448131358u && u < 3264175144u) || u >= 4080218931u);
+        }
+        for (int q = 0; q < 3; q++) { s = (s * mul[q] + add[q]) & mask; s ^= s >> sh; d = (d * mul[q] + add[q]) & mask; d ^= d >> sh; }
+        out[i * stride] = (uint32_t) (s ^ zero);
+        out[i * stride + 1] = (uint32_t) (d ^ zero);
+        if (weighted) out[i * stride + 2] = (uint32_t) ((splitmix64(ctr + 31) >> 33) % 128ull) + 1u;
+    }
+}

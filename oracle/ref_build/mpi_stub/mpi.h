@@ -236,8 +236,26 @@ inline bool progress_recv(int src) {
     complete:
         if (rx.req) s.reqs[rx.req].done = true;
         else {
-            Unexpected u; u.src = src; u.tag = rx.h.tag; u.comm = rx.h.comm; u.data.swap(rx.tmp);
-            s.unexpected.push_back(std::move(u));
+            /* a receive may have been posted while this message was still streaming in */
+            int late = 0;
+            auto& order = recv_order();
+            for (auto it = order.begin(); it != order.end(); ++it) {
+                Pending& p = s.reqs[*it];
+                if (p.peer == src && p.tag == rx.h.tag && p.comm == rx.h.comm) { late = *it; order.erase(it); break; }
+            }
+            bool earlier_unexpected = false;   /* keep arrival order among same-envelope messages */
+            for (auto& u : s.unexpected)
+                if (u.src == src && u.tag == rx.h.tag && u.comm == rx.h.comm) earlier_unexpected = true;
+            if (late && !earlier_unexpected) {
+                if (s.reqs[late].bytes < rx.h.bytes) die("message longer than posted receive");
+                memcpy(s.reqs[late].buf, rx.tmp.data(), rx.h.bytes);
+                s.reqs[late].done = true;
+                rx.tmp.clear();
+            } else {
+                if (late) order.push_front(late);
+                Unexpected u; u.src = src; u.tag = rx.h.tag; u.comm = rx.h.comm; u.data.swap(rx.tmp);
+                s.unexpected.push_back(std::move(u));
+            }
         }
         rx.have_header = false; rx.hgot = 0; rx.got = 0; rx.req = 0;
     }

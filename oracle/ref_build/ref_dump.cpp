@@ -57,6 +57,7 @@
 
 static std::string g_prefix;
 static bool g_tiles = false;
+static int g_repeat = 1;      /* --repeat R: run the timed execute() R times on the loaded graph (bench.py --impl reference) */
 
 template <typename T>
 static void write_raw(const std::string& path, const T* p, size_t n) {
@@ -139,6 +140,7 @@ int main(int argc, char** argv) {
         std::string a = argv[i];
         if (a == "--dump" && i + 1 < argc) g_prefix = argv[++i];
         else if (a == "--tiles") g_tiles = true;
+        else if (a == "--repeat" && i + 1 < argc) g_repeat = atoi(argv[++i]);
         else if (a == "--ct" && i + 1 < argc) {
             std::string c = argv[++i];
             have_ct = true;
@@ -200,6 +202,12 @@ int main(int argc, char** argv) {
     V.checksum();
     dump_states(V, ".deg");
     Env::barrier();
+    for (int rep = 1; rep < g_repeat; rep++) {        /* extra timed runs: same calls, fresh program each time */
+        PR_Program<wp, ip, fp> W(G, true, false, false, _ROW_);
+        W.initialize(V);
+        W.execute(arg3);
+        W.free();
+    }
     PR_Program<wp, ip, fp> VR(G, true, false, false, _ROW_);
     VR.initialize(V);
     V.free();

@@ -1,0 +1,51 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/graphtap_b200.h declares, and
+refuses to compute without a B200 (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from graphtap_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "graphtap_b200.h")).read()
+    return re.findall(r"^GT_API [^;(]*?\b(gt_[a-z0-9_]+)\(", hdr, flags=re.M)
+
+
+def test_header_and_binding_agree():
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    assert sorted(syms) == sorted(capi.PROTOTYPES)
+
+
+def test_every_declared_symbol_is_exported():
+    l = capi.lib()
+    for s in declared_symbols():
+        assert hasattr(l, s), s
+    assert l.gt_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = C.c_void_p()
+    st = capi.lib().gt_ctx_create(0, 0, 1, None, C.byref(ctx))
+    assert st == capi.GT_ERR_NO_DEVICE
+    assert b"no CPU fallback" in capi.lib().gt_last_error()
+    with pytest.raises(capi.GraphTapError):
+        capi.check(st)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must not route through the CPU oracle (parity would be void)."""
+    pkg = os.path.join(ROOT, "graphtap_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "gt_oracle" not in txt and "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f

@@ -1,0 +1,283 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden per-vertex dumps of the
+unmodified reference, the CPU oracle on seeded inputs, tile arrays, single-kernel checks, edge cases
+and size-independent properties.  Bit-exact for BFS/CC/SSSP/Deg and every index array; PageRank within
+1e-6 relative per vertex (BASELINE.json north_star)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PR_RTOL = 1e-6      # north_star: "within 1e-6 relative per-vertex error for PageRank ranks"
+
+
+def _E():
+    from graphtap_b200 import engine
+    return engine
+
+
+def _O():
+    from oracle import oracle
+    return oracle
+
+
+def loader(tri, n):
+    def load(G, **fl):
+        ct = fl.pop("compression_type")
+        G.load_triples(tri, n, compression_type=ct, **fl)
+    return load
+
+
+def run_gpu(app, tri, n, arg=None, compression=None):
+    E = _E()
+    if app == "pr":
+        G, V = E.run_pr(loader(tri, n), 20 if arg is None else arg, **({"compression": compression} if compression else {}))
+    elif app == "bfs":
+        G, V = E.run_bfs(loader(tri, n), arg or 0)
+    elif app == "cc":
+        G, V = E.run_cc(loader(tri, n))
+    else:
+        G, V = E.run_sssp(loader(tri, n), arg or 0)
+    states, it, cs, tm = V.V, V.iteration, V.checksum(quiet=True), V.timing()
+    V.free(); G.free()
+    return states, it, cs, tm
+
+
+def assert_states(app, mine, ref, n):
+    if app == "pr":
+        assert (mine["degree"][:n] == ref["degree"][:n]).all()
+        rel = np.abs(mine["rank"][:n] - ref["rank"][:n]) / np.abs(ref["rank"][:n])
+        assert rel.max() <= PR_RTOL, rel.max()
+    elif app == "bfs":
+        for f in ("parent", "hops", "vid"):
+            assert (mine[f][:n] == ref[f][:n]).all(), f
+    else:
+        m = mine[mine.dtype.names[0]] if mine.dtype.names else mine
+        assert (m[:n] == ref[:n]).all()
+
+
+@pytest.mark.parametrize("app", ["pr", "bfs", "cc", "sssp"])
+def test_fixture_vs_reference_dump(app, fixture_unweighted, fixture_weighted, golden_fixture):
+    tri = fixture_weighted if app == "sssp" else fixture_unweighted
+    mine, it, cs, _ = run_gpu(app, tri, 1024)
+    meta = golden_fixture[f"{app}_np1_meta"]
+    assert it == meta[0]
+    assert_states(app, mine, golden_fixture[f"{app}_np1_V"], 1025)
+    assert cs == (meta[1], meta[2])            # Value checksum / Reachable vertices lines
+
+
+def test_pr_tcsc_equals_tcsc_cf(fixture_unweighted, golden_fixture):
+    E = _E()
+    a, _, _, _ = run_gpu("pr", fixture_unweighted, 1024, 20, compression=E._TCSC_)
+    b, _, _, _ = run_gpu("pr", fixture_unweighted, 1024, 20, compression=E._TCSC_CF_)
+    assert (a["rank"] == b["rank"]).all()
+
+
+@pytest.mark.parametrize("app", ["pr", "bfs", "cc", "sssp"])
+def test_rmat12_vs_reference_dump(app, rmat12, golden_rmat12):
+    tri = rmat12 if app == "sssp" else rmat12[:, :2].copy()
+    mine, it, _, _ = run_gpu(app, tri, 4096)
+    assert it == golden_rmat12[f"{app}_np1_meta"][0]
+    assert_states(app, mine, golden_rmat12[f"{app}_np1_V"], 4097)
+
+
+@pytest.mark.parametrize("scale,seed", [(14, 1), (16, 2), (18, 3)])
+@pytest.mark.parametrize("app", ["pr", "bfs", "cc", "sssp"])
+def test_seeded_rmat_vs_oracle(app, scale, seed):
+    from graphtap_b200.rmat import rmat_edges
+    O = _O()
+    tri = rmat_edges(scale, seed=seed, weighted=(app == "sssp"))
+    n = 1 << scale
+    ref, rit = O.run_app(app, tri, n, 1, 20 if app == "pr" else (None if app == "cc" else 0))
+    mine, it, cs, tm = run_gpu(app, tri, n)
+    assert it == rit
+    assert_states(app, mine, ref, n + 1)
+    assert cs == O.checksum(app, ref, n + 1)
+    if app != "pr":
+        assert tm.sparse_iterations >= 1          # the frontier SpMSpV really ran
+
+
+@pytest.mark.parametrize("root", [1, 77, 4095])
+def test_roots(root, rmat12):
+    O = _O()
+    for app in ("bfs", "sssp"):
+        tri = rmat12 if app == "sssp" else rmat12[:, :2].copy()
+        ref, rit = O.run_app(app, tri, 4096, 1, root)
+        mine, it, _, _ = run_gpu(app, tri, 4096, root)
+        assert it == rit
+        assert_states(app, mine, ref, 4097)
+
+
+@pytest.mark.parametrize("app", ["pr", "bfs", "sssp"])
+def test_tiles_vs_oracle(app, rmat12):
+    """Device-built TCSC arrays and index maps, array by array (unweighted: bit-identical to
+    TCSC_BASE::populate; weighted: same per-column {row: min weight})."""
+    E, O = _E(), _O()
+    tri = rmat12 if app == "sssp" else rmat12[:, :2].copy()
+    fl = dict(O.APP_FLAGS[app]); w = fl.pop("weighted")
+    og = O.OracleGraph(tri, 4096, 1, weighted=w, **fl)
+    G = E.Graph(weighted=bool(w))
+    G.load_triples(tri, 4096, compression_type=E._TCSC_, **{k: bool(v) for k, v in fl.items()})
+    t, ot = G.tile(0), og.tile(0, 0)
+    np.testing.assert_array_equal(t["JC"], og.seg(True, 0)["ids"])
+    np.testing.assert_array_equal(t["IR"], og.seg(False, 0)["ids"])
+    I, IV, nr = G.rowgrp_maps(0)
+    J, JV, nc = G.colgrp_maps(0)
+    np.testing.assert_array_equal(I, og.seg(False, 0)["bits"]); np.testing.assert_array_equal(IV, og.seg(False, 0)["prefix"])
+    np.testing.assert_array_equal(J, og.seg(True, 0)["bits"]); np.testing.assert_array_equal(JV, og.seg(True, 0)["prefix"])
+    assert t["nnz"] == ot["nnz"] == G.info().nnz_local
+    np.testing.assert_array_equal(t["JA"], ot["JA"])
+    if not w:
+        np.testing.assert_array_equal(t["IA"], ot["IA"])
+    else:
+        for j in range(0, nc, 7):
+            a = sorted(zip(t["IA"][t["JA"][j]:t["JA"][j + 1]], t["A"][t["JA"][j]:t["JA"][j + 1]]))
+            b = sorted(zip(ot["IA"][ot["JA"][j]:ot["JA"][j + 1]], ot["A"][ot["JA"][j]:ot["JA"][j + 1]]))
+            assert a == b
+    G.free(); og.close()
+
+
+@pytest.mark.parametrize("semiring", ["plus_times", "min_select", "min_plus"])
+def test_single_tile_kernels_vs_oracle(semiring, rmat12):
+    """gt_tile_spmv (push and pull) and gt_tile_spmspv on random vectors, one launch each."""
+    E, O = _E(), _O()
+    from graphtap_b200 import capi
+    rng = np.random.default_rng(5)
+    w = semiring == "min_plus"
+    tri = rmat12 if w else rmat12[:, :2].copy()
+    fl = dict(directed=True, transpose=True, self_loops=True, acyclic=False, parallel_edges=not w)
+    og = O.OracleGraph(tri, 4096, 1, weighted=int(w), **{k: int(v) for k, v in fl.items()})
+    G = E.Graph(weighted=w)
+    G.load_triples(tri, 4096, compression_type=E._TCSC_, **fl)
+    nc, nr = og.seg(True, 0)["nnz"], og.seg(False, 0)["nnz"]
+    if semiring == "plus_times":
+        x = rng.random(nc); y0 = rng.random(nr)
+        ref = y0.copy(); og.spmv_f64(0, 0, x, ref, 0)
+        dx, dy = E.DeviceArray(x), E.DeviceArray(y0)
+        capi.check(capi.lib().gt_tile_spmv(G.handle, 0, capi.GT_PLUS_TIMES_F64, capi.GT_ROW, dx.ptr, dy.ptr))
+        np.testing.assert_allclose(dy.download(np.float64, nr), ref, rtol=1e-12)
+        # pull (_COL_): y over columns, x over rows
+        xr = rng.random(nr); yc0 = rng.random(nc)
+        ref = yc0.copy(); og.spmv_f64(0, 0, xr, ref, 1)
+        dx2, dy2 = E.DeviceArray(xr), E.DeviceArray(yc0)
+        capi.check(capi.lib().gt_tile_spmv(G.handle, 0, capi.GT_PLUS_TIMES_F64, capi.GT_COL, dx2.ptr, dy2.ptr))
+        np.testing.assert_allclose(dy2.download(np.float64, nc), ref, rtol=1e-12)
+        for d in (dx, dy, dx2, dy2):
+            d.free()
+    else:
+        sr = capi.GT_MIN_PLUS_U32 if w else capi.GT_MIN_SELECT_U32
+        x = rng.integers(0, 1 << 20, nc, dtype=np.uint32)
+        x[rng.random(nc) < 0.5] = O.INF
+        y0 = rng.integers(0, 1 << 21, nr, dtype=np.uint32)
+        ref = y0.copy(); og.spmv_u32(0, 0, x, ref)
+        dx, dy = E.DeviceArray(x), E.DeviceArray(y0)
+        capi.check(capi.lib().gt_tile_spmv(G.handle, 0, sr, capi.GT_ROW, dx.ptr, dy.ptr))
+        np.testing.assert_array_equal(dy.download(np.uint32, nr), ref)
+        # frontier: same result from the (xi, xv) form, plus the touched flags
+        xi = np.nonzero(x != O.INF)[0].astype(np.uint32); rng.shuffle(xi)
+        xv = x[xi]
+        ref2 = y0.copy(); tref = np.zeros(nr, dtype=np.uint8); og.spmspv_u32(0, 0, xi, xv, ref2, tref)
+        assert (ref2 == ref).all()
+        dy.upload(y0)
+        dxi, dxv, dt = E.DeviceArray(xi), E.DeviceArray(xv), E.DeviceArray(np.zeros(nr, dtype=np.uint8))
+        capi.check(capi.lib().gt_tile_spmspv(G.handle, 0, sr, dxi.ptr, dxv.ptr, len(xi), dy.ptr, dt.ptr))
+        np.testing.assert_array_equal(dy.download(np.uint32, nr), ref2)
+        np.testing.assert_array_equal(dt.download(np.uint8, nr), tref)
+        for d in (dx, dy, dxi, dxv, dt):
+            d.free()
+    G.free(); og.close()
+
+
+def test_edge_cases():
+    """Empty and degenerate inputs the reference's code paths allow."""
+    O = _O()
+    cases = {
+        "empty": (np.zeros((0, 2), dtype="<u4"), 8),
+        "self_loop_only": (np.array([[3, 3]], dtype="<u4"), 8),
+        "duplicates": (np.array([[1, 2], [2, 1], [1, 2], [1, 2], [5, 6], [0, 7]], dtype="<u4"), 8),
+        "star_hub": (np.stack([np.zeros(5000, dtype="<u4"), np.arange(1, 5001, dtype="<u4")], axis=1), 5001),
+        "chain": (np.stack([np.arange(0, 300, dtype="<u4"), np.arange(1, 301, dtype="<u4")], axis=1), 301),
+        "max_vertex_id": (np.array([[0, 1023], [1023, 0], [1023, 1023]], dtype="<u4"), 1023),
+    }
+    for name, (tri, n) in cases.items():
+        for app in ("pr", "bfs", "cc"):
+            ref, rit = O.run_app(app, tri, n, 1, 5 if app == "pr" else (None if app == "cc" else 0))
+            mine, it, _, _ = run_gpu(app, tri, n, 5 if app == "pr" else None)
+            assert it == rit, (name, app)
+            assert_states(app, mine, ref, n + 1)
+        w = np.concatenate([tri, ((np.arange(len(tri), dtype="<u4") * 37) % 128 + 1)[:, None]], axis=1).astype("<u4")
+        ref, rit = O.run_app("sssp", w, n, 1, 0)
+        mine, it, _, _ = run_gpu("sssp", w, n)
+        assert it == rit, name
+        assert_states("sssp", mine, ref, n + 1)
+
+
+def test_state_round_trip_and_checksum(fixture_unweighted):
+    E = _E()
+    G, VR = E.run_pr(loader(fixture_unweighted, 1024), 3)
+    V = VR.V
+    V2 = V.copy(); V2["rank"] *= 2.0
+    VR.set_V(V2)
+    back = VR.V
+    assert (back["rank"] == V2["rank"]).all() and (back["degree"] == V["degree"]).all()
+    VR.free(); G.free()
+
+
+def test_out_of_range_vertex_is_an_error():
+    E = _E()
+    from graphtap_b200 import capi
+    G = E.Graph()
+    with pytest.raises(capi.GraphTapError):
+        G.load_triples(np.array([[0, 5000]], dtype="<u4"), 8)
+
+
+def test_properties_at_scale_20():
+    """Size-independent properties at a size the CPU oracle would take too long for in a unit test:
+    BFS tree consistency, SSSP fixed point over every edge, CC = minimum id of the component's BFS
+    closure, PageRank is a fixed-point iterate (one more iteration from the 19-iteration state)."""
+    from graphtap_b200.rmat import rmat_edges
+    E = _E()
+    scale = 20
+    n = 1 << scale
+    tri = rmat_edges(scale, nedges=4 << scale, seed=11, weighted=True)
+    u, v, w = tri[:, 0].astype(np.int64), tri[:, 1].astype(np.int64), tri[:, 2].astype(np.int64)
+    # BFS (undirected, no self loops)
+    bfs, it, _, _ = run_gpu("bfs", tri[:, :2].copy(), n)
+    hops = bfs["hops"][: n + 1].astype(np.int64); par = bfs["parent"][: n + 1].astype(np.int64)
+    reach = hops != 2147483647
+    assert hops[0] == 0 and par[0] == 0
+    nz = np.nonzero(reach)[0]; nz = nz[nz != 0]
+    assert (hops[par[nz]] + 1 == hops[nz]).all()
+    m = u != v
+    both = reach[u[m]] & reach[v[m]]
+    assert (reach[u[m]] == reach[v[m]]).all()                     # an edge never leaves the reached set
+    assert (np.abs(hops[u[m]][both] - hops[v[m]][both]) <= 1).all()
+    # parent is the minimum-id neighbour one level up (bfs.h:61-63 min-combiner at discovery)
+    best = np.full(n + 1, np.iinfo(np.int64).max)
+    for a, b in ((u[m], v[m]), (v[m], u[m])):
+        ok = reach[a] & reach[b] & (hops[a] + 1 == hops[b])
+        np.minimum.at(best, b[ok], a[ok])
+    assert (best[nz] == par[nz]).all()
+    # CC: labels constant on edges, equal to the smallest id carrying that label
+    cc, _, _, _ = run_gpu("cc", tri[:, :2].copy(), n)
+    lab = cc["label"][: n + 1].astype(np.int64)
+    assert (lab[u] == lab[v]).all() and (lab[lab] == lab).all() and (lab <= np.arange(n + 1)).all()
+    # SSSP (directed src -> dst, weights in [1,128]): no edge can relax further, every finite distance is tight
+    ss, _, _, _ = run_gpu("sssp", tri, n)
+    d = ss["distance"][: n + 1].astype(np.int64)
+    fin = d != 2147483647
+    mm = (u != v) & fin[u]
+    assert fin[v[mm]].all() and (d[v[mm]] <= d[u[mm]] + w[mm]).all()
+    tight = np.full(n + 1, np.iinfo(np.int64).max); tight[0] = 0
+    np.minimum.at(tight, v[mm], d[u[mm]] + w[mm])
+    assert (tight[fin] == d[fin]).all()
+    # PageRank: 20 iterations == 19 iterations + 1 through the state hand-over
+    G, P = E.run_pr(loader(tri[:, :2].copy(), n), 20)
+    r20 = P.V
+    P.free(); G.free()
+    G, P = E.run_pr(loader(tri[:, :2].copy(), n), 19)
+    P.execute(20)                                                  # continues from iteration 19 to 20
+    r19p1 = P.V
+    P.free(); G.free()
+    np.testing.assert_allclose(r19p1["rank"], r20["rank"], rtol=1e-9)
