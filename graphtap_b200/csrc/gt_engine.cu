@@ -19,6 +19,7 @@
 // every rank rebuilds the frontier list locally; the 0.6 rule still picks SpMSpV vs dense SpMV per
 // column segment (:1475), so `sparse_iterations` matches the reference's schedule.
 #include "gt_kernels.cuh"
+#include "gt_pull.h"
 #include <cub/cub.cuh>
 #include <memory>
 #include <algorithm>
@@ -266,7 +267,12 @@ struct gt_program {
     gt::DevBuf<double> rank;
     gt::DevBuf<uint32_t> a, b;
     gt::DevBuf<uint8_t> C;
-    std::vector<gt::DevBuf<uint8_t>> X, Y;         // raw bytes, |x|*esize
+    struct Span { uint8_t* p = nullptr; size_t n = 0; };
+    gt::DevBuf<uint8_t> Xcat;                      // all local x segments back to back + one trailing zero element
+    std::vector<Span> X;                           // views into Xcat, |x|*esize bytes each
+    std::vector<gt::DevBuf<uint8_t>> Y;            // raw bytes, |y|*esize
+    int pr_layout = 1;                             // 1: derived pull layout for the plus-times SpMV (gt_pull.cu), 0: push over TCSC
+    const gt::PullLayout* pull = nullptr;          // owned by the graph
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
     gt::DevBuf<unsigned long long> d_active;      // [0] active count
     gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
@@ -304,7 +310,18 @@ static void prog_alloc(gt_program* P) {
     P->C.alloc(P->th);
     P->X.resize(P->pcol->size());
     P->Y.resize(P->prow->size());
-    for (size_t k = 0; k < P->X.size(); k++) P->X[k].alloc((size_t) (*P->pcol)[k].nnz * P->esize());
+    {
+        size_t total = 0;
+        for (size_t k = 0; k < P->X.size(); k++) total += (*P->pcol)[k].nnz;
+        P->Xcat.alloc((total + 1) * P->esize());
+        GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, P->ctx->stream));      // x[total] stays 0: the pull layout's padding target
+        size_t off = 0;
+        for (size_t k = 0; k < P->X.size(); k++) {
+            P->X[k].p = P->Xcat.p + off * P->esize();
+            P->X[k].n = (size_t) (*P->pcol)[k].nnz * P->esize();
+            off += (*P->pcol)[k].nnz;
+        }
+    }
     for (size_t k = 0; k < P->Y.size(); k++) P->Y[k].alloc((size_t) (*P->prow)[k].nnz * P->esize());
     if (!P->stationary) {
         P->XI.resize(P->X.size()); P->XV.resize(P->X.size());
@@ -333,6 +350,12 @@ static void prog_initialize(gt_program* P) {
         }
     }
     GT_CUDA(cudaGetLastError());
+    // PageRank's plus-times SpMV runs as a pull over the derived layout (gt_pull.cu) unless pr_layout = 0
+    P->pull = nullptr;
+    if (P->app == GT_APP_PR && P->ordering == GT_ROW && !P->g->weighted && P->pr_layout == 1) {
+        if (!P->g->pull) P->g->pull = pull_build(P->g);
+        P->pull = P->g->pull;
+    }
     P->initialized = true;
     P->iteration = 0;
     P->converged = false;
@@ -363,7 +386,8 @@ static void scatter_gather(gt_program* P) {
     const SegMaps& own = (*P->pcol)[P->own_col_slot];
     if (own.nnz) {
         const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (double*) P->X[P->own_col_slot].p);
+        const uint32_t* jc = P->pull ? P->pull->col_hot_local[P->own_col_slot].p : own.ids.p;     // pull layout: x in hot order
+        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, jc, own.nnz, (double*) P->X[P->own_col_slot].p);
         else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
         ctx->kernel_launches++;
     }
@@ -398,13 +422,16 @@ static void combine(gt_program* P) {
     if (P->stationary)                            // std::fill(y, 0) (:1026-1032)
         for (size_t k = 0; k < P->Y.size(); k++)
             if (P->Y[k].n) GT_CUDA(cudaMemsetAsync(P->Y[k].p, 0, P->Y[k].n, st));
+    if (P->pull) {
+        for (size_t k = 0; k < P->Y.size(); k++) pull_spmv(ctx, P->pull, (uint32_t) k, (const double*) P->Xcat.p, (double*) P->Y[k].p);
+    }
     bool any_sparse = false;
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
     for (const Tile& T : g->tiles) {
         const uint32_t xs = (P->ordering == GT_ROW) ? T.col_slot : T.row_slot;
         const uint32_t ys = (P->ordering == GT_ROW) ? T.row_slot : T.col_slot;
-        if (!T.nnz) continue;
+        if (!T.nnz || P->pull) continue;
         if (P->stationary) {
             launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
         } else {
@@ -440,7 +467,8 @@ static void apply(gt_program* P) {
     if (!P->stationary) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (own.nnz) {
         const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
+        const uint32_t* ir = P->pull ? P->pull->row_hot_local[P->own_row_slot].p : own.ids.p;     // pull layout: y in hot order
+        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, ir, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
         else k_apply_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, own.ids.p, own.nnz, (const uint32_t*) P->Y[P->own_row_slot].p, P->iteration, P->d_active.p);
         ctx->kernel_launches++;
     }
@@ -510,7 +538,7 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         if (n == "activity_filtering_ratio") p->activity_filtering_ratio = value;
         else if (n == "timing") p->timing = value != 0;
         else if (n == "iteration") { p->iteration = (uint32_t) value; p->converged = false; }   // public member, vertex_program.hpp:60
-        else if (n == "pr_layout") { /* selected in a later pass of this file */ }
+        else if (n == "pr_layout") { p->pr_layout = (int) value; p->initialized = false; }
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
 }
@@ -538,6 +566,9 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         const bool check = num_iterations == 0;
         const uint64_t launches0 = ctx->kernel_launches;
         const uint64_t dense_bytes = gt::algorithmic_bytes_dense(p);
+        p->tm.bytes_algorithmic = 0;
+        p->tm.sparse_iterations = 0;
+        const uint32_t it0 = p->iteration;
         GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         while (true) {
             gt::scatter_gather(p);
@@ -556,7 +587,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         GT_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         p->tm.execute_ms = ms;
         p->tm.kernel_launches = ctx->kernel_launches - launches0;
-        p->tm.iterations = p->iteration;
+        p->tm.iterations = p->iteration - it0;
         if (iters_done) *iters_done = p->iteration;
     });
 }

@@ -22,6 +22,9 @@ struct Tile {
     DevBuf<uint32_t> chunk_col;    // first column of every GT_PUSH_CHUNK-edge chunk (+ sentinel)
 };
 
+struct PullLayout;
+void pull_free(PullLayout* P);
+
 }  // namespace gt
 
 struct gt_graph {
@@ -35,6 +38,8 @@ struct gt_graph {
     std::vector<gt::SegMaps> rows, cols;     // by local slot
     std::vector<gt::Tile> tiles;             // local_tiles_row_order
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
+    gt::PullLayout* pull = nullptr;          // derived layout of the plus-times SpMV, built on first use (gt_pull.cu)
+    ~gt_graph() { if (pull) gt::pull_free(pull); }
 };
 
 // edges per CTA work item of the load-balanced push kernels (gt_kernels.cu)

@@ -1,0 +1,385 @@
+// gt_pull.cu — the plus-times SpMV of the stationary programs (PageRank) as a PULL over a layout derived
+// from the TCSC tiles, designed for what a B200 can and cannot do (profiles/r01_microbench_*.log):
+//
+//   * f64 RED.ADD into y collapses to 6-20 Gop/s under RMAT's row skew (hub rows serialise in L2), while
+//     random 8-byte gathers run at 275-565 Gop/s from L2 and ~1000 Gop/s from shared memory.  So the
+//     reference's push loop  y[IA[i]] += x[j]  (src/vp/vertex_program.hpp:1164-1172) is turned around:
+//     every row sums its own x values, no atomics on the common path.
+//   * Columns of every x segment are renumbered by decreasing group-wide degree ("hot order").  The
+//     hottest columns of each local segment live in shared memory for the whole pass (one copy per SM),
+//     the next few million stay L2-resident because they are packed densely, only the cold tail goes to
+//     HBM.  TCSC already renumbers columns to the dense range of non-empty ones
+//     (src/ds/compressed_column.hpp:381-407); this is one more order-changing renumbering of the same
+//     kind, applied consistently on all ranks of a column group (the order is a pure function of the
+//     group-wide column degrees), so x still travels compressed.
+//   * Rows are renumbered by decreasing group-wide degree too and stored as SELL-32: 32 consecutive rows
+//     form a slice, stored column-major, so lane l of a warp walks row l of the slice with perfectly
+//     coalesced 128-byte index loads and neighbouring lanes have (nearly) equal trip counts.  Rows longer
+//     than kVRow entries are cut into virtual rows whose partial sums meet in y through one RED.ADD each
+//     (<= degree/kVRow per row), which bounds the skew a warp can see.
+//
+// Results: each row's sum is formed in a fixed order by one lane (split rows excepted), so it differs from
+// the reference's column-order sum only by f64 rounding, ~1e-16 relative — inside the 1e-6 contract.
+#include "gt_pull.h"
+#include <cub/cub.cuh>
+#include <algorithm>
+
+namespace gt {
+
+static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) {
+    uint64_t g = (n + block - 1) / block;
+    uint64_t cap = (uint64_t) sm_count * per_sm;
+    return (int) std::max<uint64_t>(1, std::min(g, cap));
+}
+
+// ---- build kernels -------------------------------------------------------------------------------------
+__global__ void k_col_degrees(const uint32_t* __restrict__ JA, uint32_t ncols, uint32_t* __restrict__ deg) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) deg[j] += JA[j + 1] - JA[j];
+}
+__global__ void k_row_degrees(const uint32_t* __restrict__ IA, uint64_t nnz, uint32_t* __restrict__ deg) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < nnz; e += (uint64_t) gridDim.x * blockDim.x) atomicAdd(deg + IA[e], 1u);
+}
+// key = (~degree, id): ascending sort = decreasing degree, ties by id
+__global__ void k_hot_keys(const uint32_t* __restrict__ deg, uint32_t n, uint64_t* __restrict__ keys) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        keys[i] = ((uint64_t) (0xffffffffu - deg[i]) << 32) | i;
+}
+// from sorted keys: rank_of[id] = k, hot_local[k] = ids[id] (compressed id -> local vertex id)
+__global__ void k_hot_maps(const uint64_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ ids, uint32_t* __restrict__ rank_of,
+                           uint32_t* __restrict__ hot_local) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t id = (uint32_t) keys[k];
+        rank_of[id] = k;
+        hot_local[k] = ids[id];
+    }
+}
+// column code: < hot_total -> shared-memory slot, else hot_total + index into the concatenated x buffer
+__global__ void k_col_codes(const uint32_t* __restrict__ rank_of, uint32_t n, uint32_t slot, uint32_t hot_per_seg, uint32_t hot_total,
+                            uint32_t xoff, uint32_t* __restrict__ code) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t r = rank_of[j];
+        code[j] = r < hot_per_seg ? slot * hot_per_seg + r : hot_total + xoff + r;
+    }
+}
+// one (row', colcode) key per stored entry of a tile
+__global__ void k_expand(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, uint64_t nnz, uint32_t ncols,
+                         const uint32_t* __restrict__ col_code, const uint32_t* __restrict__ row_rank, uint64_t* __restrict__ keys) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < nnz; e += (uint64_t) gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = ncols;                      // upper_bound(JA, e) - 1 = the column that holds entry e
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t) JA[mid] <= e) lo = mid + 1; else hi = mid;
+        }
+        keys[e] = ((uint64_t) row_rank[IA[e]] << 32) | col_code[lo - 1];
+    }
+}
+__global__ void k_row_ptr(const uint64_t* __restrict__ keys, uint64_t n, uint32_t nrows, uint64_t* __restrict__ rowptr) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r <= nrows; r += gridDim.x * blockDim.x) {
+        const uint64_t target = (uint64_t) r << 32;
+        uint64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (keys[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        rowptr[r] = lo;
+    }
+}
+__global__ void k_vrow_counts(const uint64_t* __restrict__ rowptr, uint32_t nrows, uint32_t vlen, uint32_t* __restrict__ nv) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        const uint64_t len = rowptr[r + 1] - rowptr[r];
+        nv[r] = (uint32_t) std::max<uint64_t>(1, (len + vlen - 1) / vlen);
+    }
+}
+__global__ void k_vrow_make(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ vbase, uint32_t nrows, uint32_t vlen,
+                            uint32_t* __restrict__ vkey, uint32_t* __restrict__ vid) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        const uint64_t len = rowptr[r + 1] - rowptr[r];
+        const uint32_t b = vbase[r], n = vbase[r + 1] - b;
+        for (uint32_t c = 0; c < n; c++) {
+            const uint64_t l = std::min<uint64_t>(vlen, len - (uint64_t) c * vlen);
+            vkey[b + c] = vlen - (uint32_t) l;           // ascending sort = decreasing length
+            vid[b + c] = b + c;
+        }
+    }
+}
+// per sorted virtual row: start in the CSR key array, length, target row (+ split flag)
+__global__ void k_vrow_meta(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ vbase, uint32_t nrows, uint32_t vlen,
+                            const uint32_t* __restrict__ rank_of_v, uint64_t* __restrict__ vstart, uint32_t* __restrict__ vl, uint32_t* __restrict__ vtgt) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+        const uint64_t len = rowptr[r + 1] - rowptr[r];
+        const uint32_t b = vbase[r], n = vbase[r + 1] - b;
+        for (uint32_t c = 0; c < n; c++) {
+            const uint32_t pos = rank_of_v[b + c];
+            vstart[pos] = rowptr[r] + (uint64_t) c * vlen;
+            vl[pos] = (uint32_t) std::min<uint64_t>(vlen, len - (uint64_t) c * vlen);
+            vtgt[pos] = r | (n > 1 ? kPullSplit : 0u);
+        }
+    }
+}
+__global__ void k_invert(const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ inv) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv[perm[i]] = i;
+}
+__global__ void k_slice_sizes(const uint32_t* __restrict__ vl, uint32_t nv, uint32_t nslices, uint64_t* __restrict__ sizes) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= nslices; s += gridDim.x * blockDim.x)
+        sizes[s] = (s < nslices) ? 32ull * vl[(uint64_t) s * 32] : 0ull;     // rows are sorted by decreasing length
+}
+// SELL-32 fill: one warp per slice, lane l copies virtual row 32 s + l column-major
+__global__ void __launch_bounds__(256) k_sell_fill(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vstart, const uint32_t* __restrict__ vl,
+                                                    uint32_t nv, const uint64_t* __restrict__ slice_ptr, uint32_t nslices, uint32_t pad_code,
+                                                    uint32_t* __restrict__ sell) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t s = warp; s < nslices; s += nwarps) {
+        const uint64_t base = slice_ptr[s];
+        const uint32_t L = (uint32_t) ((slice_ptr[s + 1] - base) >> 5);
+        const uint32_t v = s * 32 + lane;
+        const uint32_t len = v < nv ? vl[v] : 0;
+        const uint64_t st = v < nv ? vstart[v] : 0;
+        for (uint32_t k = 0; k < L; k++) sell[base + (uint64_t) k * 32 + lane] = k < len ? (uint32_t) keys[st + k] : pad_code;
+    }
+}
+__global__ void k_count_nonzero_slices(const uint64_t* __restrict__ slice_ptr, uint32_t nslices, unsigned int* __restrict__ out) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nslices; s += gridDim.x * blockDim.x)
+        if (slice_ptr[s + 1] > slice_ptr[s]) atomicMax(out, s + 1);
+}
+
+// ---- the hot kernel ----------------------------------------------------------------------------------------
+// Persistent CTAs, one per SM.  Prologue: the hot x values of every local column segment -> shared memory.
+// Then each warp takes slices round-robin (slices are sorted by decreasing length, so every warp gets the
+// same mix of long and short ones).  Inner loop, per lane: 8 independent 4-byte index loads (streaming,
+// coalesced across the warp), 8 independent gathers (shared memory for hot codes, read-only global for the
+// rest), 8 adds.  One coalesced store of y per slice; virtual rows of split rows use RED.ADD.
+template <int UNROLL>
+__global__ void __launch_bounds__(kPullThreads, 1)
+k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
+                 const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, PullHot hot, double* __restrict__ y) {
+    extern __shared__ double xs[];
+    for (uint32_t i = threadIdx.x; i < hot.total; i += blockDim.x) {
+        const uint32_t s = i / hot.per_seg, k = i - s * hot.per_seg;
+        xs[i] = k < hot.seg_len[s] ? x[hot.xoff[s] + k] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    const double* xc = x - hot.total;                   // code - hot.total indexes x
+    for (uint32_t s = warp; s < nslices; s += nwarps) {
+        const uint64_t base = slice_ptr[s];
+        const uint32_t L = (uint32_t) ((slice_ptr[s + 1] - base) >> 5);
+        const uint32_t* p = sell + base + lane;
+        double acc = 0.0;
+        uint32_t k = 0;
+        for (; k + UNROLL <= L; k += UNROLL) {
+            uint32_t c[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) c[u] = ld_stream_u32(p + (uint64_t) (k + u) * 32);
+            double v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) v[u] = c[u] < hot.total ? xs[c[u]] : __ldg(xc + c[u]);
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) acc += v[u];
+        }
+        for (; k < L; k++) {
+            const uint32_t c = ld_stream_u32(p + (uint64_t) k * 32);
+            acc += c < hot.total ? xs[c] : __ldg(xc + c);
+        }
+        const uint32_t v = s * 32 + lane;
+        if (v < nv) {
+            const uint32_t t = vtgt[v];
+            if (t & kPullSplit) atomicAdd(y + (t & ~kPullSplit), acc);
+            else y[t] = acc;
+        }
+    }
+}
+
+// ---- build ---------------------------------------------------------------------------------------------------
+static void sort_u64(gt_ctx* ctx, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& alt, uint64_t n, int end_bit, uint64_t** sorted) {
+    cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
+    size_t tb = 0;
+    GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t) n, 0, end_bit, ctx->stream));
+    DevBuf<uint8_t> tmp; tmp.alloc(tb);
+    GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) n, 0, end_bit, ctx->stream));
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->kernel_launches += 4;
+    *sorted = db.Current();
+}
+
+// hot order of one segment from its (group-wide) degrees
+static void hot_order(gt_ctx* ctx, const DevBuf<uint32_t>& deg, uint32_t n, const uint32_t* ids, DevBuf<uint32_t>& rank_of, DevBuf<uint32_t>& hot_local) {
+    rank_of.alloc(n); hot_local.alloc(n);
+    if (!n) return;
+    DevBuf<uint64_t> keys, alt; keys.alloc(n); alt.alloc(n);
+    k_hot_keys<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(deg.p, n, keys.p);
+    uint64_t* sorted = nullptr;
+    sort_u64(ctx, keys, alt, n, 64, &sorted);
+    k_hot_maps<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(sorted, n, ids, rank_of.p, hot_local.p);
+    ctx->kernel_launches += 2;
+    GT_CUDA(cudaGetLastError());
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+PullLayout* pull_build(gt_graph* g) {
+    gt_ctx* ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    GT_REQUIRE(!g->weighted, "pull layout: unweighted graphs only");
+    std::unique_ptr<PullLayout> P(new PullLayout());
+    const size_t S = g->cols.size(), R = g->rows.size();
+    GT_REQUIRE(S <= kPullMaxSegs, "pull layout: too many local column segments");
+
+    // concatenated x space
+    P->xoff.resize(S + 1, 0);
+    for (size_t k = 0; k < S; k++) P->xoff[k + 1] = P->xoff[k] + g->cols[k].nnz;
+    P->xlen = P->xoff[S];
+    GT_REQUIRE((uint64_t) P->xlen + kPullHotDoubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
+    P->hot.per_seg = (uint32_t) (kPullHotDoubles / S);
+    P->hot.total = P->hot.per_seg * (uint32_t) S;
+    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? g->cols[k].nnz : 0; }
+    const uint32_t pad_code = P->hot.total + P->xlen;         // x[xlen] is a permanent 0.0
+
+    // 1. group-wide degrees -> hot orders
+    P->col_rank.resize(S); P->col_hot_local.resize(S); P->col_code.resize(S);
+    for (size_t k = 0; k < S; k++) {
+        const uint32_t n = g->cols[k].nnz;
+        DevBuf<uint32_t> deg; deg.alloc(n);
+        if (n) GT_CUDA(cudaMemsetAsync(deg.p, 0, (size_t) n * 4, st));
+        for (const Tile& T : g->tiles)
+            if (T.col_slot == k && T.nnz) { k_col_degrees<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, n, deg.p); ctx->kernel_launches++; }
+        if (ctx->comm && n && comm_size_in(ctx->comm, COMM_COLGRP) > 1) comm_allreduce(ctx->comm, COMM_COLGRP, deg.p, deg.p, n, CT_U32, CO_SUM, st);
+        hot_order(ctx, deg, n, g->cols[k].ids.p, P->col_rank[k], P->col_hot_local[k]);
+        P->col_code[k].alloc(n);
+        if (n) {
+            k_col_codes<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->col_rank[k].p, n, (uint32_t) k, P->hot.per_seg, P->hot.total, P->xoff[k], P->col_code[k].p);
+            ctx->kernel_launches++;
+        }
+    }
+    P->row_rank.resize(R); P->row_hot_local.resize(R); P->rows.resize(R);
+    for (size_t k = 0; k < R; k++) {
+        const uint32_t n = g->rows[k].nnz;
+        DevBuf<uint32_t> deg; deg.alloc(n);
+        if (n) GT_CUDA(cudaMemsetAsync(deg.p, 0, (size_t) n * 4, st));
+        for (const Tile& T : g->tiles)
+            if (T.row_slot == k && T.nnz) { k_row_degrees<<<grid_for(T.nnz, 256, ctx->sm_count), 256, 0, st>>>(g->IA_pool.p + T.offset, T.nnz, deg.p); ctx->kernel_launches++; }
+        if (ctx->comm && n && comm_size_in(ctx->comm, COMM_ROWGRP) > 1) comm_allreduce(ctx->comm, COMM_ROWGRP, deg.p, deg.p, n, CT_U32, CO_SUM, st);
+        hot_order(ctx, deg, n, g->rows[k].ids.p, P->row_rank[k], P->row_hot_local[k]);
+    }
+    GT_CUDA(cudaGetLastError());
+
+    // 2. per row slot: expand -> sort by (row', code) -> virtual rows -> SELL-32
+    int code_bits = 1;
+    while (code_bits < 32 && (1ull << code_bits) <= (uint64_t) pad_code) code_bits++;
+    for (size_t k = 0; k < R; k++) {
+        PullRows& Q = P->rows[k];
+        const uint32_t nr = g->rows[k].nnz;
+        Q.nrows = nr;
+        uint64_t total = 0;
+        for (const Tile& T : g->tiles) if (T.row_slot == k) total += T.nnz;
+        Q.nnz = total;
+        if (!nr || !total) continue;
+        DevBuf<uint64_t> keys, alt; keys.alloc(total); alt.alloc(total);
+        uint64_t off = 0;
+        for (const Tile& T : g->tiles) {
+            if (T.row_slot != k || !T.nnz) continue;
+            k_expand<<<grid_for(T.nnz, 256, ctx->sm_count, 16), 256, 0, st>>>(T.JA.p, g->IA_pool.p + T.offset, T.nnz, g->cols[T.col_slot].nnz,
+                                                                          P->col_code[T.col_slot].p, P->row_rank[k].p, keys.p + off);
+            ctx->kernel_launches++;
+            off += T.nnz;
+        }
+        GT_CUDA(cudaGetLastError());
+        int row_bits = 1;
+        while (row_bits < 32 && (1ull << row_bits) < nr) row_bits++;
+        uint64_t* sorted = nullptr;
+        // rows occupy bits [32, 32+row_bits); codes bits [0, code_bits): sort the low field, then the high one
+        {
+            cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
+            size_t tb = 0, tb2 = 0;
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t) total, 0, code_bits, st));
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb2, db, (int64_t) total, 32, 32 + row_bits, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(std::max(tb, tb2));
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) total, 0, code_bits, st));
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb2, db, (int64_t) total, 32, 32 + row_bits, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            ctx->kernel_launches += 8;
+            sorted = db.Current();
+        }
+        DevBuf<uint64_t> rowptr; rowptr.alloc((size_t) nr + 1);
+        k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, total, nr, rowptr.p);
+        // virtual rows
+        DevBuf<uint32_t> nvr; nvr.alloc((size_t) nr + 1);
+        GT_CUDA(cudaMemsetAsync(nvr.p + nr, 0, 4, st));
+        k_vrow_counts<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, nr, kPullVRow, nvr.p);
+        DevBuf<uint32_t> vbase; vbase.alloc((size_t) nr + 1);
+        {
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        uint32_t nv = 0;
+        GT_CUDA(cudaMemcpyAsync(&nv, vbase.p + nr, 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        Q.nv = nv;
+        DevBuf<uint32_t> vkey, vkey_alt, vid, vid_alt;
+        vkey.alloc(nv); vkey_alt.alloc(nv); vid.alloc(nv); vid_alt.alloc(nv);
+        k_vrow_make<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kPullVRow, vkey.p, vid.p);
+        uint32_t* vid_sorted = nullptr;
+        {
+            int lb = 1;
+            while ((1u << lb) <= kPullVRow) lb++;
+            cub::DoubleBuffer<uint32_t> dk(vkey.p, vkey_alt.p), dv(vid.p, vid_alt.p);
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t) nv, 0, lb, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t) nv, 0, lb, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            vid_sorted = dv.Current();
+        }
+        DevBuf<uint32_t> vpos; vpos.alloc(nv);          // unsorted virtual row -> sorted position
+        k_invert<<<grid_for(nv, 256, ctx->sm_count), 256, 0, st>>>(vid_sorted, nv, vpos.p);
+        DevBuf<uint64_t> vstart; vstart.alloc(nv);
+        DevBuf<uint32_t> vl; vl.alloc(nv);
+        Q.vtgt.alloc(nv);
+        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kPullVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
+        const uint32_t nslices = (nv + 31) / 32;
+        DevBuf<uint64_t> sizes; sizes.alloc((size_t) nslices + 1);
+        Q.slice_ptr.alloc((size_t) nslices + 1);
+        k_slice_sizes<<<grid_for((uint64_t) nslices + 1, 256, ctx->sm_count), 256, 0, st>>>(vl.p, nv, nslices, sizes.p);
+        {
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t sell_len = 0;
+        GT_CUDA(cudaMemcpyAsync(&sell_len, Q.slice_ptr.p + nslices, 8, cudaMemcpyDeviceToHost, st));
+        DevBuf<unsigned int> cnt; cnt.alloc(1);
+        GT_CUDA(cudaMemsetAsync(cnt.p, 0, 4, st));
+        k_count_nonzero_slices<<<grid_for(nslices, 256, ctx->sm_count), 256, 0, st>>>(Q.slice_ptr.p, nslices, cnt.p);
+        unsigned int active = 0;
+        GT_CUDA(cudaMemcpyAsync(&active, cnt.p, 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        Q.nslices = active;
+        Q.sell_len = sell_len;
+        Q.sell.alloc(sell_len);
+        k_sell_fill<<<grid_for((uint64_t) nslices * 32, 256, ctx->sm_count, 8), 256, 0, st>>>(sorted, vstart.p, vl.p, nv, Q.slice_ptr.p, active, pad_code, Q.sell.p);
+        ctx->kernel_launches += 12;
+        GT_CUDA(cudaGetLastError());
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+    GT_CUDA(cudaFuncSetAttribute(k_spmv_pull_sell<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kPullHotDoubles * sizeof(double))));
+    return P.release();
+}
+
+void pull_free(PullLayout* P) { delete P; }
+
+// y[row slot] = sum over the slot's rows; x = the concatenated, hot-ordered x buffer (x[xlen] == 0.0)
+void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, const double* x, double* y) {
+    const PullRows& Q = P->rows[row_slot];
+    if (!Q.nslices) return;
+    k_spmv_pull_sell<8><<<ctx->sm_count, kPullThreads, P->hot.total * sizeof(double), ctx->stream>>>(
+        Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, P->hot, y);
+    ctx->kernel_launches++;
+    GT_CUDA(cudaGetLastError());
+}
+
+}  // namespace gt

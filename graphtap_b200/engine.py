@@ -309,13 +309,16 @@ class SSSP_Program(Vertex_Program):
 
 
 # ---- the reference drivers, as functions (src/apps/{pr,bfs,cc,sssp}.cpp) ---------------------------------
-def run_pr(graph_loader, num_iterations=20, compression=_TCSC_CF_):
-    """src/apps/pr.cpp:26-53.  ``graph_loader(G, **flags)`` loads the edge list into ``G`` with the given flags."""
+def run_pr(graph_loader, num_iterations=20, compression=_TCSC_CF_, pr_layout=None):
+    """src/apps/pr.cpp:26-53.  ``graph_loader(G, **flags)`` loads the edge list into ``G`` with the given flags.
+    ``pr_layout``: 0 = push SpMV over the TCSC arrays, 1 = derived pull layout (library default)."""
     G = Graph(weighted=False)
     graph_loader(G, directed=True, transpose=True, self_loops=True, acyclic=False, parallel_edges=True, compression_type=compression)
     V = Deg_Program(G, True, False, False, _COL_)
     V.execute(1)
     VR = PR_Program(G, True, False, False, _ROW_)
+    if pr_layout is not None:
+        VR.set("pr_layout", pr_layout)
     VR.initialize(V)
     V.free()
     VR.execute(num_iterations)
