@@ -106,6 +106,7 @@ struct IngestParams {
     const int32_t* tile_local;       // [p*p] local tile index (row order) or -1
     uint8_t* I_all;                  // [p*th] any entry in this row    (count pass only)
     uint8_t* J_all;                  // [p*th] any entry in this column (count pass only)
+    uint32_t* deg_all;               // [p*th] entries in the vertex's row + column (count pass only)
     unsigned long long* counters;    // [0] owned entries, [1] append cursor, [2] out-of-range records
     uint64_t* keys;                  // fill pass
     uint32_t* wts;                   // fill pass, weighted
@@ -120,7 +121,7 @@ __device__ __forceinline__ void ingest_emit(const IngestParams& Q, uint32_t r, u
         rg = r / Q.th;
         cg = c / Q.th;
         t = Q.tile_local[rg * Q.p + cg];
-        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; }
+        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.deg_all + r, 1u); atomicAdd(Q.deg_all + c, 1u); }
     }
     const bool own = valid && t >= 0;
     if (!FILL) {
@@ -190,6 +191,27 @@ __global__ void k_seg_maps(const uint8_t* bits_all, const uint32_t* scan_all, ui
         const uint32_t k = scan_all[seg_base + i] - s0;
         prefix[i] = b ? k : 0;                    // matrix.hpp:1031-1040
         if (b) ids[k] = i;                        // compressed_column.hpp:399-416 (JC / IR)
+    }
+}
+
+// hot order: key = (~degree, local id) for vertices with a non-empty row or column, all-ones otherwise
+__global__ void k_hot_keys(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, const uint32_t* __restrict__ deg, uint32_t th, uint64_t* __restrict__ keys) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
+        keys[i] = (I[i] | J[i]) ? (((uint64_t) (0xffffffffu - deg[i]) << 32) | i) : ~0ull;
+}
+__global__ void k_hot_count(const uint64_t* __restrict__ keys, uint32_t th, uint32_t* __restrict__ n) {
+    uint32_t lo = 0, hi = th;                      // first all-ones key (degrees are >= 1, so real keys are smaller)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < 0xffffffff00000000ull) lo = mid + 1; else hi = mid;
+    }
+    *n = lo;
+}
+__global__ void k_hot_finish(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ ids, uint32_t* __restrict__ pos) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t id = (uint32_t) keys[k];
+        ids[k] = id;
+        pos[id] = k;
     }
 }
 
@@ -287,6 +309,8 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     I_all.alloc(nall); J_all.alloc(nall);
     GT_CUDA(cudaMemsetAsync(I_all.p, 0, nall, st));
     GT_CUDA(cudaMemsetAsync(J_all.p, 0, nall, st));
+    DevBuf<uint32_t> deg_all; deg_all.alloc(nall);
+    GT_CUDA(cudaMemsetAsync(deg_all.p, 0, nall * 4, st));
     DevBuf<unsigned long long> counters; counters.alloc(4);
     GT_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), st));
 
@@ -294,7 +318,7 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     Q.th = th; Q.p = p;
     Q.self_loops = flags->self_loops; Q.acyclic = flags->acyclic; Q.transpose = flags->transpose; Q.directed = flags->directed;
     Q.weighted = weighted; Q.bw = bw;
-    Q.tile_local = d_tile_local.p; Q.I_all = I_all.p; Q.J_all = J_all.p; Q.counters = counters.p;
+    Q.tile_local = d_tile_local.p; Q.I_all = I_all.p; Q.J_all = J_all.p; Q.deg_all = deg_all.p; Q.counters = counters.p;
     RmatParams G{};
     if (gen) G = *gen;
 
@@ -429,7 +453,42 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
         make(I_all, L.local_row_segments, g->rows);
         make(J_all, L.local_col_segments, g->cols);
     }
-    I_all.release(); J_all.release();
+    // ---- hot order of every local segment (rows and columns of a segment share it) ------------------
+    {
+        std::vector<int32_t> segs = L.local_row_segments;
+        for (int32_t c : L.local_col_segments) if (std::find(segs.begin(), segs.end(), c) == segs.end()) segs.push_back(c);
+        g->hot.resize(segs.size());
+        DevBuf<uint64_t> keys, alt; keys.alloc(th); alt.alloc(th);
+        DevBuf<uint8_t> tmp;
+        size_t tb = 0;
+        {
+            cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t) th, 0, 64, st));
+            tmp.alloc(tb);
+        }
+        DevBuf<uint32_t> d_n; d_n.alloc(1);
+        for (size_t h = 0; h < segs.size(); h++) {
+            HotOrder& H = g->hot[h];
+            H.segment = segs[h];
+            const uint64_t b = (uint64_t) segs[h] * th;
+            k_hot_keys<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(I_all.p + b, J_all.p + b, deg_all.p + b, th, keys.p);
+            cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
+            GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) th, 0, 64, st));
+            k_hot_count<<<1, 1, 0, st>>>(db.Current(), th, d_n.p);
+            GT_CUDA(cudaMemcpyAsync(&H.n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            H.ids.alloc(H.n); H.pos.alloc(th);
+            GT_CUDA(cudaMemsetAsync(H.pos.p, 0xff, (size_t) th * 4, st));
+            if (H.n) k_hot_finish<<<grid_for(H.n, 256, ctx->sm_count), 256, 0, st>>>(db.Current(), H.n, H.ids.p, H.pos.p);
+            ctx->kernel_launches += 6;
+            GT_CUDA(cudaGetLastError());
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        auto find_hot = [&](int32_t seg) { for (size_t h = 0; h < segs.size(); h++) if (segs[h] == seg) return (int) h; return -1; };
+        for (int32_t r : L.local_row_segments) g->hot_of_row_slot.push_back(find_hot(r));
+        for (int32_t c : L.local_col_segments) g->hot_of_col_slot.push_back(find_hot(c));
+    }
+    I_all.release(); J_all.release(); deg_all.release();
 
     // ---- tiles ------------------------------------------------------------------------------------
     std::vector<uint64_t> bounds(ntiles + 1, 0);

@@ -161,6 +161,54 @@ __global__ void __launch_bounds__(256) k_count_u8(const uint8_t* __restrict__ C,
     if (threadIdx.x == 0 && tot) atomicAdd(out, (unsigned long long) tot);
 }
 
+// ---- PageRank in the pull layout: the owned segment's state lives in hot order while execute() runs, so
+// applicator (pr.h:43-47) and next iteration's messenger (pr.h:31-33) are one sequential pass ------------
+__global__ void k_pr_to_hot(const uint32_t* __restrict__ ids, uint32_t n, const double* __restrict__ rank, const uint32_t* __restrict__ deg,
+                            const uint8_t* __restrict__ I, double* __restrict__ rank_h, uint32_t* __restrict__ deg_h, uint8_t* __restrict__ flag_h) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t v = ids[k];
+        rank_h[k] = rank[v]; deg_h[k] = deg[v]; flag_h[k] = I[v];
+    }
+}
+__global__ void k_pr_from_hot(const uint32_t* __restrict__ ids, uint32_t n, const double* __restrict__ rank_h, const uint8_t* __restrict__ C_h,
+                              double* __restrict__ rank, uint8_t* __restrict__ C) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t v = ids[k];
+        rank[v] = rank_h[k]; C[v] = C_h[k];
+    }
+}
+__global__ void k_pr_messenger_h(const double* __restrict__ rank_h, const uint32_t* __restrict__ deg_h, uint32_t n, double* __restrict__ x) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t d = deg_h[k];
+        x[k] = d ? rank_h[k] / (double) d : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) k_pr_apply_h(const double* __restrict__ y, double* __restrict__ rank_h, const uint32_t* __restrict__ deg_h,
+                                                     const uint8_t* __restrict__ flag_h, uint8_t* __restrict__ C_h, double* __restrict__ x, uint32_t n,
+                                                     double alpha, double tol, unsigned long long* __restrict__ active) {
+    unsigned local = 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        double r = rank_h[k];
+        uint8_t c = 0;
+        if (flag_h[k]) {                                   // row non-empty: applicator(state, y)
+            const double nw = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, y[k]));
+            c = fabs(nw - r) > tol;
+            rank_h[k] = nw;
+            r = nw;
+        }                                                  // else applicator(state) -> false (:1666-1667)
+        C_h[k] = c;
+        local += c;
+        const uint32_t d = deg_h[k];
+        x[k] = d ? r / (double) d : 0.0;                   // next iteration's messenger
+    }
+    if (active) {
+        typedef cub::BlockReduce<unsigned, 256> BR;
+        __shared__ typename BR::TempStorage tmp;
+        const unsigned tot = BR(tmp).Sum(local);
+        if (threadIdx.x == 0 && tot) atomicAdd(active, (unsigned long long) tot);
+    }
+}
+
 // initialize(other): degree hand-over where the row is non-empty (:476-483, pr.h:24-28)
 __global__ void k_init_from_deg(VState V, const uint32_t* __restrict__ other_deg, const uint8_t* __restrict__ I, uint32_t th, double alpha) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
@@ -273,6 +321,14 @@ struct gt_program {
     std::vector<gt::DevBuf<uint8_t>> Y;            // raw bytes, |y|*esize
     int pr_layout = 1;                             // 1: derived pull layout for the plus-times SpMV (gt_pull.cu), 0: push over TCSC
     const gt::PullLayout* pull = nullptr;          // owned by the graph
+    // pull mode: x / y in hot order, and the owned segment's state in hot order while execute() runs
+    gt::DevBuf<double> Xh;                         // concatenated hot-ordered x of the local column segments (+ one 0.0)
+    std::vector<gt::DevBuf<double>> Yh;            // per row slot
+    gt::DevBuf<double> rank_h;
+    gt::DevBuf<uint32_t> deg_h;
+    gt::DevBuf<uint8_t> flag_h, C_h;
+    const gt::HotOrder* own_hot = nullptr;
+    bool hot_valid = false, x_ready = false;
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
     gt::DevBuf<unsigned long long> d_active;      // [0] active count
     gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
@@ -355,7 +411,17 @@ static void prog_initialize(gt_program* P) {
     if (P->app == GT_APP_PR && P->ordering == GT_ROW && !P->g->weighted && P->pr_layout == 1) {
         if (!P->g->pull) P->g->pull = pull_build(P->g);
         P->pull = P->g->pull;
+        if (!P->Xh.p) {
+            P->Xh.alloc((size_t) P->pull->xlen + 1);
+            GT_CUDA(cudaMemsetAsync(P->Xh.p, 0, P->Xh.bytes(), st));
+            P->Yh.resize(P->pull->rows.size());
+            for (size_t k = 0; k < P->Yh.size(); k++) P->Yh[k].alloc(P->pull->rows[k].ny);
+            P->own_hot = &P->g->hot[P->g->hot_of_row_slot[P->own_row_slot]];
+            P->rank_h.alloc(P->own_hot->n); P->deg_h.alloc(P->own_hot->n); P->flag_h.alloc(P->own_hot->n); P->C_h.alloc(P->own_hot->n);
+        }
     }
+    P->hot_valid = false;
+    P->x_ready = false;
     P->initialized = true;
     P->iteration = 0;
     P->converged = false;
@@ -380,14 +446,102 @@ static uint64_t algorithmic_bytes_dense(const gt_program* P) {
     return b;
 }
 
+// natural-order state -> hot-order working state of the owned segment (once per execute)
+static void pull_state_in(gt_program* P) {
+    if (P->hot_valid) return;
+    gt_ctx* ctx = P->ctx;
+    const HotOrder& H = *P->own_hot;
+    if (H.n) {
+        const SegMaps& own = (*P->prow)[P->own_row_slot];
+        k_pr_to_hot<<<grid_for(H.n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(H.ids.p, H.n, P->rank.p, P->a.p, own.bits.p, P->rank_h.p, P->deg_h.p, P->flag_h.p);
+        ctx->kernel_launches++;
+        GT_CUDA(cudaMemsetAsync(P->C_h.p, 0, H.n, ctx->stream));
+    }
+    P->hot_valid = true;
+    P->x_ready = false;
+}
+// hot-order state -> natural-order V / C (at the end of execute)
+static void pull_state_out(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    const HotOrder& H = *P->own_hot;
+    if (!P->empty_cleared) {                          // vertices outside the hot order never see an applicator with y
+        const SegMaps& own = (*P->prow)[P->own_row_slot];
+        k_clear_C_empty<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, ctx->stream>>>(P->C.p, own.bits.p, P->th);
+        ctx->kernel_launches++;
+        P->empty_cleared = true;
+    }
+    if (H.n) {
+        k_pr_from_hot<<<grid_for(H.n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(H.ids.p, H.n, P->rank_h.p, P->C_h.p, P->rank.p, P->C.p);
+        ctx->kernel_launches++;
+    }
+    GT_CUDA(cudaGetLastError());
+}
+
+static void pull_scatter_gather(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    pull_state_in(P);
+    const uint32_t n = P->own_hot->n;
+    double* xo = P->Xh.p + P->pull->xoff[P->own_col_slot];
+    if (!P->x_ready && n) {                           // later iterations: x was written by the fused applicator
+        k_pr_messenger_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->rank_h.p, P->deg_h.p, n, xo);
+        ctx->kernel_launches++;
+    }
+    P->x_ready = true;
+    if (ctx->comm) {
+        comm_group_start(ctx->comm);
+        for (size_t k = 0; k < P->pull->xoff.size() - 1; k++) {
+            const uint32_t len = P->pull->xoff[k + 1] - P->pull->xoff[k];
+            if (!len) continue;
+            const int root = comm_index_of_world_rank(ctx->comm, P->bcast_group, P->g->lay.leader_ranks[(*P->pcol)[k].segment]);
+            comm_bcast(ctx->comm, P->bcast_group, P->Xh.p + P->pull->xoff[k], len, CT_F64, root, st);
+        }
+        comm_group_end(ctx->comm);
+    }
+    GT_CUDA(cudaGetLastError());
+}
+
+static void pull_combine(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    for (size_t k = 0; k < P->Yh.size(); k++) {
+        if (!P->Yh[k].n) continue;
+        GT_CUDA(cudaMemsetAsync(P->Yh[k].p, 0, P->Yh[k].bytes(), st));       // std::fill(y, 0) (:1026-1032)
+        pull_spmv(ctx, P->pull, (uint32_t) k, P->Xh.p, P->Yh[k].p);
+    }
+    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1) {
+        comm_group_start(ctx->comm);
+        for (size_t k = 0; k < P->Yh.size(); k++) {
+            if (!P->Yh[k].n) continue;
+            const int root = comm_index_of_world_rank(ctx->comm, P->reduce_group, P->g->lay.leader_ranks[(*P->prow)[k].segment]);
+            comm_reduce(ctx->comm, P->reduce_group, P->Yh[k].p, P->Yh[k].p, P->Yh[k].n, CT_F64, CO_SUM, root, st);
+        }
+        comm_group_end(ctx->comm);
+    }
+}
+
+static void pull_apply(gt_program* P, bool count_active) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = P->own_hot->n;
+    if (count_active) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
+    if (n) {
+        k_pr_apply_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->Yh[P->own_row_slot].p, P->rank_h.p, P->deg_h.p, P->flag_h.p, P->C_h.p,
+                                                                   P->Xh.p + P->pull->xoff[P->own_col_slot], n, P->prm.alpha, P->prm.tol,
+                                                                   count_active ? P->d_active.p : nullptr);
+        ctx->kernel_launches++;
+    }
+    GT_CUDA(cudaGetLastError());
+}
+
 static void scatter_gather(gt_program* P) {
+    if (P->pull) { pull_scatter_gather(P); return; }
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     const SegMaps& own = (*P->pcol)[P->own_col_slot];
     if (own.nnz) {
         const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        const uint32_t* jc = P->pull ? P->pull->col_hot_local[P->own_col_slot].p : own.ids.p;     // pull layout: x in hot order
-        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, jc, own.nnz, (double*) P->X[P->own_col_slot].p);
+        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (double*) P->X[P->own_col_slot].p);
         else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
         ctx->kernel_launches++;
     }
@@ -416,22 +570,20 @@ static void scatter_gather(gt_program* P) {
 }
 
 static void combine(gt_program* P) {
+    if (P->pull) { pull_combine(P); return; }
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     gt_graph* g = P->g;
     if (P->stationary)                            // std::fill(y, 0) (:1026-1032)
         for (size_t k = 0; k < P->Y.size(); k++)
             if (P->Y[k].n) GT_CUDA(cudaMemsetAsync(P->Y[k].p, 0, P->Y[k].n, st));
-    if (P->pull) {
-        for (size_t k = 0; k < P->Y.size(); k++) pull_spmv(ctx, P->pull, (uint32_t) k, (const double*) P->Xcat.p, (double*) P->Y[k].p);
-    }
     bool any_sparse = false;
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
     for (const Tile& T : g->tiles) {
         const uint32_t xs = (P->ordering == GT_ROW) ? T.col_slot : T.row_slot;
         const uint32_t ys = (P->ordering == GT_ROW) ? T.row_slot : T.col_slot;
-        if (!T.nnz || P->pull) continue;
+        if (!T.nnz) continue;
         if (P->stationary) {
             launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
         } else {
@@ -455,7 +607,8 @@ static void combine(gt_program* P) {
     }
 }
 
-static void apply(gt_program* P) {
+static void apply(gt_program* P, bool count_active = false) {
+    if (P->pull) { pull_apply(P, count_active); return; }
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     const SegMaps& own = (*P->prow)[P->own_row_slot];
@@ -467,8 +620,7 @@ static void apply(gt_program* P) {
     if (!P->stationary) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (own.nnz) {
         const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        const uint32_t* ir = P->pull ? P->pull->row_hot_local[P->own_row_slot].p : own.ids.p;     // pull layout: y in hot order
-        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, ir, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
+        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
         else k_apply_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, own.ids.p, own.nnz, (const uint32_t*) P->Y[P->own_row_slot].p, P->iteration, P->d_active.p);
         ctx->kernel_launches++;
     }
@@ -479,7 +631,7 @@ static void apply(gt_program* P) {
 static bool has_converged(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
-    if (P->stationary) {
+    if (P->stationary && !P->pull) {
         GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
         k_count_u8<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, P->th, P->d_active.p);
         ctx->kernel_launches++;
@@ -573,7 +725,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         while (true) {
             gt::scatter_gather(p);
             gt::combine(p);
-            gt::apply(p);
+            gt::apply(p, check);
             p->iteration++;
             p->tm.bytes_algorithmic += dense_bytes;
             if (check) {
@@ -581,6 +733,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
             } else if (p->iteration >= num_iterations) break;
         }
+        if (p->pull) gt::pull_state_out(p);            // hot-order working state -> V (one pass per execute, inside the timed window)
         GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
         GT_CUDA(cudaStreamSynchronize(ctx->stream));
         float ms = 0;
@@ -597,7 +750,8 @@ extern "C" int gt_program_run_phase(gt_program* p, int phase) {
         GT_REQUIRE(p && p->initialized, "gt_program_run_phase: program not initialized");
         GT_REQUIRE(phase >= 0 && phase <= 2, "gt_program_run_phase: phase must be 0, 1 or 2");
         GT_CUDA(cudaSetDevice(p->ctx->device));
-        if (phase == 0) gt::scatter_gather(p);
+        if (p->pull) gt::pull_state_in(p);
+        if (phase == 0) { p->x_ready = false; gt::scatter_gather(p); }
         else if (phase == 1) gt::combine(p);
         else gt::apply(p);
     });
@@ -633,6 +787,7 @@ extern "C" int gt_program_state_from_host(gt_program* p, const void* V_in, uint6
         if (!p->initialized) gt::prog_initialize(p);
         gt::DevBuf<uint32_t> stage; stage.alloc(need / 4);
         GT_CUDA(cudaMemcpyAsync(stage.p, V_in, need, cudaMemcpyHostToDevice, p->ctx->stream));
+        p->hot_valid = false; p->x_ready = false;
         gt::k_unpack_state<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), p->app, p->th, stage.p);
         p->ctx->kernel_launches++;
         GT_CUDA(cudaGetLastError());

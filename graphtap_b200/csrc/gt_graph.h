@@ -14,6 +14,17 @@ struct SegMaps {
     DevBuf<uint32_t> ids;          // IR / JC [nnz]          compressed id -> local id
 };
 
+// "Hot order" of one vertex segment: the vertices that have any entry in their row or column, by
+// decreasing global degree (in + out, counted at ingest over the whole edge list, so every rank derives
+// the same order without communication).  The pull layout of the plus-times SpMV indexes both x and y of
+// the segment in this order (gt_pull.cu).
+struct HotOrder {
+    int32_t segment = -1;
+    uint32_t n = 0;                // vertices in the order
+    DevBuf<uint32_t> ids;          // [n]           position -> local vertex id
+    DevBuf<uint32_t> pos;          // [tile_height] local vertex id -> position, 0xffffffff if absent
+};
+
 struct Tile {
     uint32_t rg = 0, cg = 0, row_slot = 0, col_slot = 0;
     uint64_t nnz = 0;
@@ -38,6 +49,8 @@ struct gt_graph {
     std::vector<gt::SegMaps> rows, cols;     // by local slot
     std::vector<gt::Tile> tiles;             // local_tiles_row_order
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
+    std::vector<gt::HotOrder> hot;           // one per distinct local segment
+    std::vector<int> hot_of_row_slot, hot_of_col_slot;
     gt::PullLayout* pull = nullptr;          // derived layout of the plus-times SpMV, built on first use (gt_pull.cu)
     ~gt_graph() { if (pull) gt::pull_free(pull); }
 };

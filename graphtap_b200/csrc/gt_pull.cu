@@ -5,18 +5,23 @@
 //     random 8-byte gathers run at 275-565 Gop/s from L2 and ~1000 Gop/s from shared memory.  So the
 //     reference's push loop  y[IA[i]] += x[j]  (src/vp/vertex_program.hpp:1164-1172) is turned around:
 //     every row sums its own x values, no atomics on the common path.
-//   * Columns of every x segment are renumbered by decreasing group-wide degree ("hot order").  The
-//     hottest columns of each local segment live in shared memory for the whole pass (one copy per SM),
-//     the next few million stay L2-resident because they are packed densely, only the cold tail goes to
-//     HBM.  TCSC already renumbers columns to the dense range of non-empty ones
-//     (src/ds/compressed_column.hpp:381-407); this is one more order-changing renumbering of the same
-//     kind, applied consistently on all ranks of a column group (the order is a pure function of the
-//     group-wide column degrees), so x still travels compressed.
-//   * Rows are renumbered by decreasing group-wide degree too and stored as SELL-32: 32 consecutive rows
-//     form a slice, stored column-major, so lane l of a warp walks row l of the slice with perfectly
-//     coalesced 128-byte index loads and neighbouring lanes have (nearly) equal trip counts.  Rows longer
-//     than kVRow entries are cut into virtual rows whose partial sums meet in y through one RED.ADD each
-//     (<= degree/kVRow per row), which bounds the skew a warp can see.
+//   * Every vertex segment gets ONE "hot order" (gt_graph.h HotOrder): its vertices with any entry, by
+//     decreasing global degree, computed at ingest from the whole edge list so all ranks agree without
+//     talking.  Both the x and the y vector of the segment are indexed in that order.  Hot x values are
+//     packed densely at the front, so they stay L1/L2 resident and only the cold tail goes to HBM; and
+//     because x and y of the owned segment share the order, applicator + messenger fuse into one
+//     perfectly sequential pass over the vertex state (gt_engine.cu).  TCSC already renumbers rows and
+//     columns to dense ranges (src/ds/compressed_column.hpp:381-416); this is one more renumbering of
+//     the same kind.
+//   * Rows are stored as SELL-32: virtual rows (below) sorted by decreasing length, 32 of them per slice,
+//     column-major inside the slice, so lane l of a warp walks row l with perfectly coalesced 128-byte
+//     index loads and neighbouring lanes have (nearly) equal trip counts.  Rows longer than `vrow`
+//     entries are cut into virtual rows whose partial sums meet in y through one RED.ADD each
+//     (<= degree/vrow per row), which bounds the skew a warp can see.
+//   * No shared-memory staging of x by default: a large carve-out shrinks L1, and L1's capacity bounds
+//     the number of gather misses in flight (ncu: MIO throttle 100 %, L1TEX 23 % with a 200 KB cache vs
+//     84 % without; profiles/r01_ncu_pull_s26_hot*.txt).  The kernel is bound by L1TEX sector throughput
+//     (one 32-byte sector per edge per clock per SM), which is the structural limit of a gather design.
 //
 // Results: each row's sum is formed in a fixed order by one lane (split rows excepted), so it differs from
 // the reference's column-order sum only by f64 rounding, ~1e-16 relative — inside the 1e-6 contract.
@@ -33,31 +38,15 @@ static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) 
 }
 
 // ---- build kernels -------------------------------------------------------------------------------------
-__global__ void k_col_degrees(const uint32_t* __restrict__ JA, uint32_t ncols, uint32_t* __restrict__ deg) {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) deg[j] += JA[j + 1] - JA[j];
+// compressed id -> index in the segment's hot order (composition of JC / IR with HotOrder::pos)
+__global__ void k_compose(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ pos, uint32_t add, uint32_t* __restrict__ out) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[j] = add + pos[ids[j]];
 }
-__global__ void k_row_degrees(const uint32_t* __restrict__ IA, uint64_t nnz, uint32_t* __restrict__ deg) {
-    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < nnz; e += (uint64_t) gridDim.x * blockDim.x) atomicAdd(deg + IA[e], 1u);
-}
-// key = (~degree, id): ascending sort = decreasing degree, ties by id
-__global__ void k_hot_keys(const uint32_t* __restrict__ deg, uint32_t n, uint64_t* __restrict__ keys) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        keys[i] = ((uint64_t) (0xffffffffu - deg[i]) << 32) | i;
-}
-// from sorted keys: rank_of[id] = k, hot_local[k] = ids[id] (compressed id -> local vertex id)
-__global__ void k_hot_maps(const uint64_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ ids, uint32_t* __restrict__ rank_of,
-                           uint32_t* __restrict__ hot_local) {
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const uint32_t id = (uint32_t) keys[k];
-        rank_of[id] = k;
-        hot_local[k] = ids[id];
-    }
-}
-// column code: < hot_total -> shared-memory slot, else hot_total + index into the concatenated x buffer
-__global__ void k_col_codes(const uint32_t* __restrict__ rank_of, uint32_t n, uint32_t slot, uint32_t hot_per_seg, uint32_t hot_total,
-                            uint32_t xoff, uint32_t* __restrict__ code) {
+// optional shared-memory hot cache: positions < hot_per_seg of column slot `slot` become smem slots
+__global__ void k_col_codes(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ pos, uint32_t slot, uint32_t hot_per_seg,
+                            uint32_t hot_total, uint32_t xoff, uint32_t* __restrict__ code) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t r = rank_of[j];
+        const uint32_t r = pos[ids[j]];
         code[j] = r < hot_per_seg ? slot * hot_per_seg + r : hot_total + xoff + r;
     }
 }
@@ -150,17 +139,20 @@ __global__ void k_count_nonzero_slices(const uint64_t* __restrict__ slice_ptr, u
 // coalesced across the warp), 8 independent gathers (shared memory for hot codes, read-only global for the
 // rest), 8 adds.  One coalesced store of y per slice; virtual rows of split rows use RED.ADD.
 template <int UNROLL>
-__global__ void __launch_bounds__(kPullThreads, 1)
+__global__ void __launch_bounds__(kPullThreads)
 k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
                  const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, PullHot hot, double* __restrict__ y) {
     extern __shared__ double xs[];
-    for (uint32_t i = threadIdx.x; i < hot.total; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < hot.total; i += blockDim.x) {     // hot.total == 0 when the cache is disabled
         const uint32_t s = i / hot.per_seg, k = i - s * hot.per_seg;
         xs[i] = k < hot.seg_len[s] ? x[hot.xoff[s] + k] : 0.0;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    // Slices are sorted by decreasing length.  Consecutive slices go to consecutive CTAs (not to consecutive
+    // warps of one CTA), so every SM receives the same mix of long and short slices: with the naive order the
+    // longest slices all landed on the first few SMs and the rest of the chip idled (profiles/r01_ncu_pull_v0).
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarps = gridDim.x * (blockDim.x >> 5);
     const double* xc = x - hot.total;                   // code - hot.total indexes x
     for (uint32_t s = warp; s < nslices; s += nwarps) {
         const uint64_t base = slice_ptr[s];
@@ -192,31 +184,6 @@ k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__
 }
 
 // ---- build ---------------------------------------------------------------------------------------------------
-static void sort_u64(gt_ctx* ctx, DevBuf<uint64_t>& keys, DevBuf<uint64_t>& alt, uint64_t n, int end_bit, uint64_t** sorted) {
-    cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
-    size_t tb = 0;
-    GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t) n, 0, end_bit, ctx->stream));
-    DevBuf<uint8_t> tmp; tmp.alloc(tb);
-    GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) n, 0, end_bit, ctx->stream));
-    GT_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->kernel_launches += 4;
-    *sorted = db.Current();
-}
-
-// hot order of one segment from its (group-wide) degrees
-static void hot_order(gt_ctx* ctx, const DevBuf<uint32_t>& deg, uint32_t n, const uint32_t* ids, DevBuf<uint32_t>& rank_of, DevBuf<uint32_t>& hot_local) {
-    rank_of.alloc(n); hot_local.alloc(n);
-    if (!n) return;
-    DevBuf<uint64_t> keys, alt; keys.alloc(n); alt.alloc(n);
-    k_hot_keys<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(deg.p, n, keys.p);
-    uint64_t* sorted = nullptr;
-    sort_u64(ctx, keys, alt, n, 64, &sorted);
-    k_hot_maps<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(sorted, n, ids, rank_of.p, hot_local.p);
-    ctx->kernel_launches += 2;
-    GT_CUDA(cudaGetLastError());
-    GT_CUDA(cudaStreamSynchronize(ctx->stream));
-}
-
 PullLayout* pull_build(gt_graph* g) {
     gt_ctx* ctx = g->ctx;
     cudaStream_t st = ctx->stream;
@@ -224,42 +191,42 @@ PullLayout* pull_build(gt_graph* g) {
     std::unique_ptr<PullLayout> P(new PullLayout());
     const size_t S = g->cols.size(), R = g->rows.size();
     GT_REQUIRE(S <= kPullMaxSegs, "pull layout: too many local column segments");
+    if (const char* e = getenv("GT_PULL_VROW")) P->vrow = std::max(8, atoi(e));
+    if (const char* e = getenv("GT_PULL_HOT")) P->hot_doubles = std::min(28000, std::max(0, atoi(e)));
+    if (const char* e = getenv("GT_PULL_THREADS")) P->threads = std::min(1024, std::max(32, atoi(e) / 32 * 32));
+    if (const char* e = getenv("GT_PULL_CTAS")) P->ctas_per_sm = std::min(8, std::max(1, atoi(e)));
+    const uint32_t kVRow = P->vrow;
 
-    // concatenated x space
+    // concatenated x space: the hot orders of the local column segments, back to back
     P->xoff.resize(S + 1, 0);
-    for (size_t k = 0; k < S; k++) P->xoff[k + 1] = P->xoff[k] + g->cols[k].nnz;
+    for (size_t k = 0; k < S; k++) P->xoff[k + 1] = P->xoff[k] + g->hot[g->hot_of_col_slot[k]].n;
     P->xlen = P->xoff[S];
-    GT_REQUIRE((uint64_t) P->xlen + kPullHotDoubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
-    P->hot.per_seg = (uint32_t) (kPullHotDoubles / S);
+    GT_REQUIRE((uint64_t) P->xlen + P->hot_doubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
+    P->hot.per_seg = (uint32_t) (P->hot_doubles / S);
     P->hot.total = P->hot.per_seg * (uint32_t) S;
-    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? g->cols[k].nnz : 0; }
+    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? g->hot[g->hot_of_col_slot[k]].n : 0; }
     const uint32_t pad_code = P->hot.total + P->xlen;         // x[xlen] is a permanent 0.0
 
-    // 1. group-wide degrees -> hot orders
-    P->col_rank.resize(S); P->col_hot_local.resize(S); P->col_code.resize(S);
+    // 1. compressed column id -> code, compressed row id -> y index
+    std::vector<DevBuf<uint32_t>> col_code(S), row_rank(R);
     for (size_t k = 0; k < S; k++) {
         const uint32_t n = g->cols[k].nnz;
-        DevBuf<uint32_t> deg; deg.alloc(n);
-        if (n) GT_CUDA(cudaMemsetAsync(deg.p, 0, (size_t) n * 4, st));
-        for (const Tile& T : g->tiles)
-            if (T.col_slot == k && T.nnz) { k_col_degrees<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, n, deg.p); ctx->kernel_launches++; }
-        if (ctx->comm && n && comm_size_in(ctx->comm, COMM_COLGRP) > 1) comm_allreduce(ctx->comm, COMM_COLGRP, deg.p, deg.p, n, CT_U32, CO_SUM, st);
-        hot_order(ctx, deg, n, g->cols[k].ids.p, P->col_rank[k], P->col_hot_local[k]);
-        P->col_code[k].alloc(n);
+        col_code[k].alloc(n);
         if (n) {
-            k_col_codes<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->col_rank[k].p, n, (uint32_t) k, P->hot.per_seg, P->hot.total, P->xoff[k], P->col_code[k].p);
+            k_col_codes<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(g->cols[k].ids.p, n, g->hot[g->hot_of_col_slot[k]].pos.p, (uint32_t) k,
+                                                                       P->hot.per_seg, P->hot.total, P->xoff[k], col_code[k].p);
             ctx->kernel_launches++;
         }
     }
-    P->row_rank.resize(R); P->row_hot_local.resize(R); P->rows.resize(R);
+    P->rows.resize(R);
     for (size_t k = 0; k < R; k++) {
         const uint32_t n = g->rows[k].nnz;
-        DevBuf<uint32_t> deg; deg.alloc(n);
-        if (n) GT_CUDA(cudaMemsetAsync(deg.p, 0, (size_t) n * 4, st));
-        for (const Tile& T : g->tiles)
-            if (T.row_slot == k && T.nnz) { k_row_degrees<<<grid_for(T.nnz, 256, ctx->sm_count), 256, 0, st>>>(g->IA_pool.p + T.offset, T.nnz, deg.p); ctx->kernel_launches++; }
-        if (ctx->comm && n && comm_size_in(ctx->comm, COMM_ROWGRP) > 1) comm_allreduce(ctx->comm, COMM_ROWGRP, deg.p, deg.p, n, CT_U32, CO_SUM, st);
-        hot_order(ctx, deg, n, g->rows[k].ids.p, P->row_rank[k], P->row_hot_local[k]);
+        row_rank[k].alloc(n);
+        P->rows[k].ny = g->hot[g->hot_of_row_slot[k]].n;
+        if (n) {
+            k_compose<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(g->rows[k].ids.p, n, g->hot[g->hot_of_row_slot[k]].pos.p, 0, row_rank[k].p);
+            ctx->kernel_launches++;
+        }
     }
     GT_CUDA(cudaGetLastError());
 
@@ -268,8 +235,7 @@ PullLayout* pull_build(gt_graph* g) {
     while (code_bits < 32 && (1ull << code_bits) <= (uint64_t) pad_code) code_bits++;
     for (size_t k = 0; k < R; k++) {
         PullRows& Q = P->rows[k];
-        const uint32_t nr = g->rows[k].nnz;
-        Q.nrows = nr;
+        const uint32_t nr = Q.ny;          // rows are addressed by y index (position in the segment's hot order)
         uint64_t total = 0;
         for (const Tile& T : g->tiles) if (T.row_slot == k) total += T.nnz;
         Q.nnz = total;
@@ -279,7 +245,7 @@ PullLayout* pull_build(gt_graph* g) {
         for (const Tile& T : g->tiles) {
             if (T.row_slot != k || !T.nnz) continue;
             k_expand<<<grid_for(T.nnz, 256, ctx->sm_count, 16), 256, 0, st>>>(T.JA.p, g->IA_pool.p + T.offset, T.nnz, g->cols[T.col_slot].nnz,
-                                                                          P->col_code[T.col_slot].p, P->row_rank[k].p, keys.p + off);
+                                                                          col_code[T.col_slot].p, row_rank[k].p, keys.p + off);
             ctx->kernel_launches++;
             off += T.nnz;
         }
@@ -305,7 +271,7 @@ PullLayout* pull_build(gt_graph* g) {
         // virtual rows
         DevBuf<uint32_t> nvr; nvr.alloc((size_t) nr + 1);
         GT_CUDA(cudaMemsetAsync(nvr.p + nr, 0, 4, st));
-        k_vrow_counts<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, nr, kPullVRow, nvr.p);
+        k_vrow_counts<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, nr, kVRow, nvr.p);
         DevBuf<uint32_t> vbase; vbase.alloc((size_t) nr + 1);
         {
             size_t tb = 0;
@@ -320,11 +286,11 @@ PullLayout* pull_build(gt_graph* g) {
         Q.nv = nv;
         DevBuf<uint32_t> vkey, vkey_alt, vid, vid_alt;
         vkey.alloc(nv); vkey_alt.alloc(nv); vid.alloc(nv); vid_alt.alloc(nv);
-        k_vrow_make<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kPullVRow, vkey.p, vid.p);
+        k_vrow_make<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vkey.p, vid.p);
         uint32_t* vid_sorted = nullptr;
         {
             int lb = 1;
-            while ((1u << lb) <= kPullVRow) lb++;
+            while ((1u << lb) <= kVRow) lb++;
             cub::DoubleBuffer<uint32_t> dk(vkey.p, vkey_alt.p), dv(vid.p, vid_alt.p);
             size_t tb = 0;
             GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t) nv, 0, lb, st));
@@ -338,7 +304,7 @@ PullLayout* pull_build(gt_graph* g) {
         DevBuf<uint64_t> vstart; vstart.alloc(nv);
         DevBuf<uint32_t> vl; vl.alloc(nv);
         Q.vtgt.alloc(nv);
-        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kPullVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
+        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
         const uint32_t nslices = (nv + 31) / 32;
         DevBuf<uint64_t> sizes; sizes.alloc((size_t) nslices + 1);
         Q.slice_ptr.alloc((size_t) nslices + 1);
@@ -366,7 +332,7 @@ PullLayout* pull_build(gt_graph* g) {
         GT_CUDA(cudaGetLastError());
         GT_CUDA(cudaStreamSynchronize(st));
     }
-    GT_CUDA(cudaFuncSetAttribute(k_spmv_pull_sell<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kPullHotDoubles * sizeof(double))));
+    GT_CUDA(cudaFuncSetAttribute(k_spmv_pull_sell<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (28000 * sizeof(double))));
     return P.release();
 }
 
@@ -376,7 +342,7 @@ void pull_free(PullLayout* P) { delete P; }
 void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, const double* x, double* y) {
     const PullRows& Q = P->rows[row_slot];
     if (!Q.nslices) return;
-    k_spmv_pull_sell<8><<<ctx->sm_count, kPullThreads, P->hot.total * sizeof(double), ctx->stream>>>(
+    k_spmv_pull_sell<8><<<ctx->sm_count * P->ctas_per_sm, P->threads, P->hot.total * sizeof(double), ctx->stream>>>(
         Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, P->hot, y);
     ctx->kernel_launches++;
     GT_CUDA(cudaGetLastError());

@@ -5,32 +5,33 @@
 namespace gt {
 
 constexpr uint32_t kPullMaxSegs = 8;            // local column segments per rank (rank_ncolgrps: 1,2,2,4 at p = 1,2,4,8)
-constexpr uint32_t kPullHotDoubles = 25600;     // 200 KB of shared memory for the hot x values
-constexpr uint32_t kPullVRow = 2048;            // longest run of entries one lane sums before the row is split
+constexpr uint32_t kPullVRow = 512;             // longest run of entries one lane sums before the row is split (GT_PULL_VROW)
 constexpr uint32_t kPullSplit = 0x80000000u;    // vtgt flag: partial sum of a split row -> RED.ADD
 constexpr int kPullThreads = 1024;
 
-struct PullHot {                                // passed by value to the kernel
+struct PullHot {                                // optional shared-memory copy of the hottest x values (off by default)
     uint32_t total, per_seg;
     uint32_t xoff[kPullMaxSegs];                // start of segment s in the concatenated x buffer
     uint32_t seg_len[kPullMaxSegs];
 };
 
 struct PullRows {                               // one local row segment
-    uint32_t nrows = 0, nv = 0, nslices = 0;
+    uint32_t ny = 0;                            // length of its y vector = vertices in the segment's hot order
+    uint32_t nv = 0, nslices = 0;
     uint64_t nnz = 0, sell_len = 0;
     DevBuf<uint32_t> sell;                      // SELL-32 column codes, slice-major then column-major
     DevBuf<uint64_t> slice_ptr;                 // [nslices_all + 1]
-    DevBuf<uint32_t> vtgt;                      // [nv] hot row id (| kPullSplit)
+    DevBuf<uint32_t> vtgt;                      // [nv] y index (| kPullSplit)
 };
 
 struct PullLayout {
-    std::vector<uint32_t> xoff;                 // [S + 1] concatenated x offsets
-    uint32_t xlen = 0;
+    std::vector<uint32_t> xoff;                 // [S + 1] offsets of the local column segments in the concatenated x
+    uint32_t xlen = 0;                          // x[xlen] is a permanent 0.0 (padding target)
     PullHot hot{};
-    std::vector<DevBuf<uint32_t>> col_rank, col_hot_local, col_code;   // per column slot
-    std::vector<DevBuf<uint32_t>> row_rank, row_hot_local;             // per row slot
-    std::vector<PullRows> rows;
+    std::vector<PullRows> rows;                 // per row slot
+    uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
+    uint32_t hot_doubles = 0;
+    int threads = kPullThreads, ctas_per_sm = 2;
 };
 
 PullLayout* pull_build(gt_graph* g);
