@@ -85,6 +85,9 @@ class Env:
         if cls.ctx is not None:
             check(lib().gt_ctx_destroy(cls.ctx))
             cls.ctx = None
+        if cls._dist is not None and cls._dist.is_initialized():
+            cls._dist.destroy_process_group()
+            cls._dist = None
 
     @classmethod
     def print_time(cls, preamble: str, seconds: float) -> None:
