@@ -1,0 +1,36 @@
+"""The source-compatible C++ shim (include/graphtap/graphtap.hpp): apps/gt_apps.cpp makes the reference
+drivers' calls and must print the reference's own checksum lines on the reference's own fixtures."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "apps", "gt_apps")
+G = os.path.join(ROOT, "tests", "golden")
+EXPECT = {  # Iterations / Value checksum / Reachable vertices
+    "pr": ("rmat10_1024.bin", "20", (20, 70, 1025)),
+    "bfs": ("rmat10_1024.bin", "0", (4, 1912, 887)),
+    "cc": ("rmat10_1024.bin", None, (4, 69590, 1025)),
+    "sssp": ("rmat10_1024_w.bin", "0", (7, 53366, 471)),
+}
+
+
+def test_shim_compiles_against_the_c_abi():
+    subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "apps", "gt_apps.cpp")], check=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("app", sorted(EXPECT))
+def test_cpp_driver_prints_reference_checksums(app):
+    f, arg, (it, cs, reach) = EXPECT[app]
+    cmd = [EXE, app, os.path.join(G, f), "1024"] + ([arg] if arg else [])
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
+    get = lambda k: int([l for l in out.splitlines() if l.startswith(k)][-1].split()[-1])
+    assert (get("Iterations:"), get("Value checksum:"), get("Reachable vertices:")) == (it, cs, reach)
+    if app == "bfs":
+        assert "vertex[1]:Parent=317,Hops=2" in out and "vertex[5]:Parent=866,Hops=3" in out
+    if app == "pr":
+        assert "vertex[4]:Rank=1.238176,Degree=2" in out and "vertex[5]:Rank=0.150000,Degree=0" in out
+    if app == "sssp":
+        assert "vertex[2]:Distance=INF" in out and "vertex[9]:Distance=116" in out
