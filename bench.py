@@ -213,7 +213,15 @@ def run_ours(args):
     tm = P.timing()
     iter_bytes = tm.bytes_algorithmic / max(1, tm.iterations)
     iter_ms = sum(step_ms) / len(step_ms) / ITERS
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the SpMV kernel, one ncu --set full capture per launch
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = f"pagerank_rmat{scale}_p{nranks}"
+        if key in t:
+            traffic = t[key]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "combine phase = y zero-fill + SpMV over the local tiles", "kernel_ms": phases[1], "kernel_algorithmic_bytes": kb,
                 "peak_source": peak_src,
                 "iteration_algorithmic_bytes": iter_bytes, "iteration_ms": iter_ms,

@@ -34,6 +34,8 @@ struct Nccl {
     ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -60,6 +62,8 @@ static Nccl& nccl() {
     n.Broadcast = (decltype(n.Broadcast)) sym("ncclBroadcast");
     n.Reduce = (decltype(n.Reduce)) sym("ncclReduce");
     n.AllReduce = (decltype(n.AllReduce)) sym("ncclAllReduce");
+    n.AllGather = (decltype(n.AllGather)) sym("ncclAllGather");
+    n.ReduceScatter = (decltype(n.ReduceScatter)) sym("ncclReduceScatter");
     n.GroupStart = (decltype(n.GroupStart)) sym("ncclGroupStart");
     n.GroupEnd = (decltype(n.GroupEnd)) sym("ncclGroupEnd");
     n.GetErrorString = (decltype(n.GetErrorString)) sym("ncclGetErrorString");
@@ -135,6 +139,16 @@ void comm_bcast(Comm* c, CommGroup g, void* buf, size_t count, CommType t, int r
 }
 void comm_reduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, int root, cudaStream_t s) {
     GT_NCCL(nccl().Reduce(send, recv, count, nccl_type(t), nccl_op(op), root, pick(c, g), s));
+}
+// in place: rank r contributes buf[r*count .. (r+1)*count) and receives everything
+void comm_allgather_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, cudaStream_t s) {
+    const size_t es = t == CT_F64 || t == CT_U64 ? 8 : t == CT_U32 ? 4 : 1;
+    GT_NCCL(nccl().AllGather((const char*) buf + (size_t) comm_rank_in(c, g) * count * es, buf, count, nccl_type(t), pick(c, g), s));
+}
+// in place: every rank passes size*count elements, rank r ends up with the reduction of chunk r at buf[r*count ..)
+void comm_reduce_scatter_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, CommOp op, cudaStream_t s) {
+    const size_t es = t == CT_F64 || t == CT_U64 ? 8 : t == CT_U32 ? 4 : 1;
+    GT_NCCL(nccl().ReduceScatter(buf, (char*) buf + (size_t) comm_rank_in(c, g) * count * es, count, nccl_type(t), nccl_op(op), pick(c, g), s));
 }
 void comm_allreduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, cudaStream_t s) {
     GT_NCCL(nccl().AllReduce(send, recv, count, nccl_type(t), nccl_op(op), pick(c, g), s));

@@ -323,11 +323,12 @@ struct gt_program {
     const gt::PullLayout* pull = nullptr;          // owned by the graph
     // pull mode: x / y in hot order, and the owned segment's state in hot order while execute() runs
     gt::DevBuf<double> Xh;                         // concatenated hot-ordered x of the local column segments (+ one 0.0)
-    std::vector<gt::DevBuf<double>> Yh;            // per row slot
+    gt::DevBuf<double> Yh;                         // concatenated y chunks of the local row segments
     gt::DevBuf<double> rank_h;
     gt::DevBuf<uint32_t> deg_h;
     gt::DevBuf<uint8_t> flag_h, C_h;
     const gt::HotOrder* own_hot = nullptr;
+    gt::DevBuf<uint32_t> stage;                    // AoS staging of V for gt_program_state_{to,from}_host (kept: no malloc per call)
     bool hot_valid = false, x_ready = false;
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
     gt::DevBuf<unsigned long long> d_active;      // [0] active count
@@ -414,8 +415,7 @@ static void prog_initialize(gt_program* P) {
         if (!P->Xh.p) {
             P->Xh.alloc((size_t) P->pull->xlen + 1);
             GT_CUDA(cudaMemsetAsync(P->Xh.p, 0, P->Xh.bytes(), st));
-            P->Yh.resize(P->pull->rows.size());
-            for (size_t k = 0; k < P->Yh.size(); k++) P->Yh[k].alloc(P->pull->rows[k].ny);
+            P->Yh.alloc(P->pull->ylen);
             P->own_hot = &P->g->hot[P->g->hot_of_row_slot[P->own_row_slot]];
             P->rank_h.alloc(P->own_hot->n); P->deg_h.alloc(P->own_hot->n); P->flag_h.alloc(P->own_hot->n); P->C_h.alloc(P->own_hot->n);
         }
@@ -488,36 +488,19 @@ static void pull_scatter_gather(gt_program* P) {
         ctx->kernel_launches++;
     }
     P->x_ready = true;
-    if (ctx->comm) {
-        comm_group_start(ctx->comm);
-        for (size_t k = 0; k < P->pull->xoff.size() - 1; k++) {
-            const uint32_t len = P->pull->xoff[k + 1] - P->pull->xoff[k];
-            if (!len) continue;
-            const int root = comm_index_of_world_rank(ctx->comm, P->bcast_group, P->g->lay.leader_ranks[(*P->pcol)[k].segment]);
-            comm_bcast(ctx->comm, P->bcast_group, P->Xh.p + P->pull->xoff[k], len, CT_F64, root, st);
-        }
-        comm_group_end(ctx->comm);
-    }
+    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)       // every member leads exactly one of the group's segments
+        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xh.p, P->pull->xchunk, CT_F64, st);
     GT_CUDA(cudaGetLastError());
 }
 
 static void pull_combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
-    for (size_t k = 0; k < P->Yh.size(); k++) {
-        if (!P->Yh[k].n) continue;
-        GT_CUDA(cudaMemsetAsync(P->Yh[k].p, 0, P->Yh[k].bytes(), st));       // std::fill(y, 0) (:1026-1032)
-        pull_spmv(ctx, P->pull, (uint32_t) k, P->Xh.p, P->Yh[k].p);
-    }
-    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1) {
-        comm_group_start(ctx->comm);
-        for (size_t k = 0; k < P->Yh.size(); k++) {
-            if (!P->Yh[k].n) continue;
-            const int root = comm_index_of_world_rank(ctx->comm, P->reduce_group, P->g->lay.leader_ranks[(*P->prow)[k].segment]);
-            comm_reduce(ctx->comm, P->reduce_group, P->Yh[k].p, P->Yh[k].p, P->Yh[k].n, CT_F64, CO_SUM, root, st);
-        }
-        comm_group_end(ctx->comm);
-    }
+    if (P->Yh.n) GT_CUDA(cudaMemsetAsync(P->Yh.p, 0, P->Yh.bytes(), st));     // std::fill(y, 0) (:1026-1032)
+    for (size_t k = 0; k < P->pull->rows.size(); k++)
+        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
+    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
+        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, P->pull->ychunk, CT_F64, CO_SUM, st);
 }
 
 static void pull_apply(gt_program* P, bool count_active) {
@@ -526,7 +509,7 @@ static void pull_apply(gt_program* P, bool count_active) {
     const uint32_t n = P->own_hot->n;
     if (count_active) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (n) {
-        k_pr_apply_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->Yh[P->own_row_slot].p, P->rank_h.p, P->deg_h.p, P->flag_h.p, P->C_h.p,
+        k_pr_apply_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->Yh.p + P->pull->yoff[P->own_row_slot], P->rank_h.p, P->deg_h.p, P->flag_h.p, P->C_h.p,
                                                                    P->Xh.p + P->pull->xoff[P->own_col_slot], n, P->prm.alpha, P->prm.tol,
                                                                    count_active ? P->d_active.p : nullptr);
         ctx->kernel_launches++;
@@ -769,7 +752,8 @@ extern "C" int gt_program_state_to_host(gt_program* p, void* V_out, uint64_t cap
         const uint64_t bytes = (uint64_t) p->th * gt_program_state_bytes(p);
         GT_REQUIRE(cap_bytes >= bytes, "gt_program_state_to_host: buffer too small");
         GT_CUDA(cudaSetDevice(p->ctx->device));
-        gt::DevBuf<uint32_t> stage; stage.alloc(bytes / 4);
+        if (p->stage.n < bytes / 4) p->stage.alloc(bytes / 4);
+        gt::DevBuf<uint32_t>& stage = p->stage;
         gt::k_pack_state<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), p->app, p->th, p->vid0, stage.p);
         p->ctx->kernel_launches++;
         GT_CUDA(cudaGetLastError());
@@ -785,7 +769,8 @@ extern "C" int gt_program_state_from_host(gt_program* p, const void* V_in, uint6
         GT_REQUIRE(bytes == need, "gt_program_state_from_host: size is not tile_height states");
         GT_CUDA(cudaSetDevice(p->ctx->device));
         if (!p->initialized) gt::prog_initialize(p);
-        gt::DevBuf<uint32_t> stage; stage.alloc(need / 4);
+        if (p->stage.n < need / 4) p->stage.alloc(need / 4);
+        gt::DevBuf<uint32_t>& stage = p->stage;
         GT_CUDA(cudaMemcpyAsync(stage.p, V_in, need, cudaMemcpyHostToDevice, p->ctx->stream));
         p->hot_valid = false; p->x_ready = false;
         gt::k_unpack_state<<<gt::grid_for(p->th, 256, p->ctx->sm_count), 256, 0, p->ctx->stream>>>(p->vs(), p->app, p->th, stage.p);

@@ -117,6 +117,8 @@ void comm_group_start(Comm* c);
 void comm_group_end(Comm* c);
 void comm_bcast(Comm* c, CommGroup g, void* buf, size_t count, CommType t, int root, cudaStream_t s);
 void comm_reduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, int root, cudaStream_t s);
+void comm_allgather_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, cudaStream_t s);
+void comm_reduce_scatter_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, CommOp op, cudaStream_t s);
 void comm_allreduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, cudaStream_t s);
 
 }  // namespace gt

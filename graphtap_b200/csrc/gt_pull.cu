@@ -197,14 +197,26 @@ PullLayout* pull_build(gt_graph* g) {
     if (const char* e = getenv("GT_PULL_CTAS")) P->ctas_per_sm = std::min(8, std::max(1, atoi(e)));
     const uint32_t kVRow = P->vrow;
 
-    // concatenated x space: the hot orders of the local column segments, back to back
-    P->xoff.resize(S + 1, 0);
-    for (size_t k = 0; k < S; k++) P->xoff[k + 1] = P->xoff[k] + g->hot[g->hot_of_col_slot[k]].n;
-    P->xlen = P->xoff[S];
-    GT_REQUIRE((uint64_t) P->xlen + P->hot_doubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
+    // concatenated x / y spaces (see PullLayout): chunk index = group rank of the segment's leader
+    P->xoff.resize(S); P->xn.resize(S); P->yoff.resize(R); P->yn.resize(R);
+    for (size_t k = 0; k < S; k++) { P->xn[k] = g->hot[g->hot_of_col_slot[k]].n; P->xchunk = std::max(P->xchunk, P->xn[k]); }
+    for (size_t k = 0; k < R; k++) { P->yn[k] = g->hot[g->hot_of_row_slot[k]].n; P->ychunk = std::max(P->ychunk, P->yn[k]); }
+    P->xchunk = (P->xchunk + 1) / 2 * 2;       // keep every chunk 16-byte aligned
+    P->ychunk = (P->ychunk + 1) / 2 * 2;
+    for (size_t k = 0; k < S; k++) {
+        const int q = ctx->comm ? comm_index_of_world_rank(ctx->comm, COMM_COLGRP, g->lay.leader_ranks[g->cols[k].segment]) : (int) k;
+        P->xoff[k] = (uint32_t) q * P->xchunk;
+    }
+    for (size_t k = 0; k < R; k++) {
+        const int q = ctx->comm ? comm_index_of_world_rank(ctx->comm, COMM_ROWGRP, g->lay.leader_ranks[g->rows[k].segment]) : (int) k;
+        P->yoff[k] = (uint32_t) q * P->ychunk;
+    }
+    GT_REQUIRE((uint64_t) S * P->xchunk + P->hot_doubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
+    P->xlen = (uint32_t) S * P->xchunk;
+    P->ylen = (uint32_t) R * P->ychunk;
     P->hot.per_seg = (uint32_t) (P->hot_doubles / S);
     P->hot.total = P->hot.per_seg * (uint32_t) S;
-    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? g->hot[g->hot_of_col_slot[k]].n : 0; }
+    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? P->xn[k] : 0; }
     const uint32_t pad_code = P->hot.total + P->xlen;         // x[xlen] is a permanent 0.0
 
     // 1. compressed column id -> code, compressed row id -> y index
@@ -222,7 +234,7 @@ PullLayout* pull_build(gt_graph* g) {
     for (size_t k = 0; k < R; k++) {
         const uint32_t n = g->rows[k].nnz;
         row_rank[k].alloc(n);
-        P->rows[k].ny = g->hot[g->hot_of_row_slot[k]].n;
+        P->rows[k].ny = P->yn[k];
         if (n) {
             k_compose<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(g->rows[k].ids.p, n, g->hot[g->hot_of_row_slot[k]].pos.p, 0, row_rank[k].p);
             ctx->kernel_launches++;

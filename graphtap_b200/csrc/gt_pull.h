@@ -25,8 +25,13 @@ struct PullRows {                               // one local row segment
 };
 
 struct PullLayout {
-    std::vector<uint32_t> xoff;                 // [S + 1] offsets of the local column segments in the concatenated x
-    uint32_t xlen = 0;                          // x[xlen] is a permanent 0.0 (padding target)
+    // Concatenated x: one equal-sized chunk per member of the column group, chunk q = the segment led by group
+    // rank q, so that the whole exchange is ONE in-place ncclAllGather (the reference: one Ibcast per segment,
+    // src/vp/vertex_program.hpp:843-862).  Same for y and the row group with ncclReduceScatter.
+    std::vector<uint32_t> xoff, xn;             // per column slot: chunk start, vertices in the segment's hot order
+    uint32_t xchunk = 0, xlen = 0;              // chunk size, total; x[xlen] is a permanent 0.0 (padding target)
+    std::vector<uint32_t> yoff, yn;             // per row slot
+    uint32_t ychunk = 0, ylen = 0;
     PullHot hot{};
     std::vector<PullRows> rows;                 // per row slot
     uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
