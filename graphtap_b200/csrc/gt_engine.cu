@@ -24,6 +24,7 @@
 #include <memory>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 
 namespace gt {
 
@@ -330,6 +331,8 @@ struct gt_program {
     const gt::HotOrder* own_hot = nullptr;
     gt::DevBuf<uint32_t> stage;                    // AoS staging of V for gt_program_state_{to,from}_host (kept: no malloc per call)
     bool hot_valid = false, x_ready = false;
+    uint64_t sparse_bytes = 0;                     // bytes_algorithmic bookkeeping of the current iteration
+    bool dense_tiles = true;
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
     gt::DevBuf<unsigned long long> d_active;      // [0] active count
     gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
@@ -560,7 +563,7 @@ static void combine(gt_program* P) {
     if (P->stationary)                            // std::fill(y, 0) (:1026-1032)
         for (size_t k = 0; k < P->Y.size(); k++)
             if (P->Y[k].n) GT_CUDA(cudaMemsetAsync(P->Y[k].p, 0, P->Y[k].n, st));
-    bool any_sparse = false;
+    bool any_sparse = false, all_sparse = !P->stationary;
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
     for (const Tile& T : g->tiles) {
@@ -573,11 +576,13 @@ static void combine(gt_program* P) {
             const uint32_t k = P->h_counts[xs];
             const uint32_t nx = (*P->pcol)[xs].nnz;
             const bool sparse = nx && ((double) k / (double) nx <= P->activity_filtering_ratio);   // :768-772
+            if (sparse) P->sparse_bytes += 16ull * k; else all_sparse = false;
             if (sparse) { any_sparse = true; launch_spmspv(ctx, g, T, P->semiring, P->XI[xs].p, P->XV[xs].p, k, P->Y[ys].p, nullptr); }
             else launch_spmv(ctx, g, T, P->semiring, P->ordering, true, P->X[xs].p, P->Y[ys].p, nullptr);
         }
     }
     if (any_sparse) P->tm.sparse_iterations++;
+    P->dense_tiles = !all_sparse;
     if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1) {
         comm_group_start(ctx->comm);
         for (size_t k = 0; k < P->Y.size(); k++) {
@@ -705,12 +710,26 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         p->tm.sparse_iterations = 0;
         const uint32_t it0 = p->iteration;
         GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
+        p->tm.scatter_gather_ms = p->tm.combine_ms = p->tm.apply_ms = 0;
+        // -DTIMING counters of the reference (:640-684,1018-1054,1611-1637): wall clock around each phase with
+        // the stream drained, only when the "timing" knob is on (it serialises host and device)
+        auto phase = [&](double& acc, auto&& fn) {
+            if (!p->timing) { fn(); return; }
+            GT_CUDA(cudaStreamSynchronize(ctx->stream));
+            const auto t0 = std::chrono::steady_clock::now();
+            fn();
+            GT_CUDA(cudaStreamSynchronize(ctx->stream));
+            acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        };
         while (true) {
-            gt::scatter_gather(p);
-            gt::combine(p);
-            gt::apply(p, check);
+            phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
+            p->sparse_bytes = 0; p->dense_tiles = true;
+            phase(p->tm.combine_ms, [&] { gt::combine(p); });
+            phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
             p->iteration++;
-            p->tm.bytes_algorithmic += dense_bytes;
+            // dense iterations move the full structure; an iteration whose tiles all took the
+            // frontier branch is counted at its lower bound (xi/xv + JA pairs of the k frontier columns)
+            p->tm.bytes_algorithmic += p->dense_tiles ? dense_bytes : p->sparse_bytes;
             if (check) {
                 p->converged = gt::has_converged(p);
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC

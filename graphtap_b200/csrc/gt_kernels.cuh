@@ -26,7 +26,9 @@ template <> struct Semiring<GT_MIN_PLUS_U32> {            // src/apps/sssp.h:49-
     typedef uint32_t T;
     __device__ static __forceinline__ T mul(T x, uint32_t w) { return x + w; }
     __device__ static __forceinline__ bool skip(T x) { return x == GT_INF_U32; }
-    __device__ static __forceinline__ void reduce(T* y, T v) { atomicMin(y, v); }     // RED.E.MIN
+    // y only ever decreases, so a (possibly stale) L2 read that is already <= v proves the RED useless;
+    // hub rows settle after a few updates and stop serialising in L2
+    __device__ static __forceinline__ void reduce(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }     // RED.E.MIN
     __device__ static __forceinline__ T identity() { return GT_INF_U32; }
     __device__ static __forceinline__ T plus(T a, T b) { return a < b ? a : b; }
 };
@@ -34,7 +36,7 @@ template <> struct Semiring<GT_MIN_SELECT_U32> {          // src/apps/bfs.h:61-6
     typedef uint32_t T;
     __device__ static __forceinline__ T mul(T x, uint32_t w) { return x + w; }      // bfs.h:56-59 (weighted build)
     __device__ static __forceinline__ bool skip(T x) { return x == GT_INF_U32; }
-    __device__ static __forceinline__ void reduce(T* y, T v) { atomicMin(y, v); }
+    __device__ static __forceinline__ void reduce(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }
     __device__ static __forceinline__ T identity() { return GT_INF_U32; }
     __device__ static __forceinline__ T plus(T a, T b) { return a < b ? a : b; }
 };

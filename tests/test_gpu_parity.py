@@ -315,3 +315,60 @@ def test_properties_at_scale_20():
     r19p1 = P.V
     P.free(); G.free()
     np.testing.assert_allclose(r19p1["rank"], r20["rank"], rtol=1e-9)
+
+
+def test_full_size_pagerank_push_vs_pull_scale24():
+    """At a size the CPU oracle cannot check in a unit test, the two independent SpMV forms (push over the
+    TCSC arrays with RED.ADD, pull over the derived SELL layout) must agree per vertex, degrees must match the
+    stored column counts, and the timing knob must report the three phases."""
+    E = _E()
+    scale = 24
+    G = E.Graph(weighted=False)
+    G.load_rmat(scale, directed=True, transpose=True, self_loops=True, parallel_edges=True, compression_type=E._TCSC_CF_)
+    assert G.info().nnz_global == 16 << scale                     # PageRank keeps duplicates and self loops
+    D = E.Deg_Program(G, True, False, False, E._COL_)
+    D.execute(1)
+    assert D.checksum(quiet=True)[0] == 16 << scale               # sum of out-degrees = stored entries
+    out = {}
+    for layout in (0, 1):
+        P = E.PR_Program(G, True, False, False, E._ROW_)
+        P.set("pr_layout", layout)
+        P.set("timing", 1)
+        P.initialize(D)
+        P.execute(20)
+        tm = P.timing()
+        assert tm.iterations == 20 and tm.combine_ms > 0 and tm.apply_ms > 0 and tm.scatter_gather_ms > 0
+        assert tm.combine_ms + tm.apply_ms + tm.scatter_gather_ms <= tm.execute_ms * 1.5 + 5
+        out[layout] = P.V
+        P.free()
+    D.free(); G.free()
+    assert (out[0]["degree"] == out[1]["degree"]).all()
+    rel = np.abs(out[0]["rank"] - out[1]["rank"]) / out[1]["rank"]
+    assert rel.max() < 1e-9, rel.max()
+    assert out[1]["rank"].min() >= 0.15 - 1e-12                   # rank = alpha + (1-alpha) * y, y >= 0
+
+
+def test_sparse_and_dense_paths_agree():
+    """activity_filtering_ratio = 0 forces the dense SpMV every iteration, 1.0 forces the frontier SpMSpV
+    whenever possible; results and iteration counts must not depend on it (src/vp/vertex_program.hpp:194,768-772)."""
+    from graphtap_b200.rmat import rmat_edges
+    E = _E()
+    tri = rmat_edges(16, seed=9, weighted=True)
+    n = 1 << 16
+    for app, mk, w, fl in (("bfs", E.BFS_Program, False, dict(directed=False, transpose=False, self_loops=False, parallel_edges=False)),
+                           ("sssp", E.SSSP_Program, True, dict(directed=True, transpose=True, self_loops=False, parallel_edges=False))):
+        G = E.Graph(weighted=w)
+        G.load_triples(tri if w else tri[:, :2].copy(), n, **fl)
+        res = {}
+        for ratio in (0.0, 0.6, 1.0):
+            V = mk(G, False, app == "sssp", app == "bfs", E._ROW_)
+            V.set("activity_filtering_ratio", ratio)
+            it = V.execute()
+            res[ratio] = (it, V.V.copy(), V.timing().sparse_iterations)
+            V.free()
+        G.free()
+        assert res[0.0][2] <= 1 and res[1.0][2] >= res[0.6][2] >= 1
+        for ratio in (0.6, 1.0):
+            assert res[ratio][0] == res[0.0][0]
+            for f in res[ratio][1].dtype.names:
+                assert (res[ratio][1][f] == res[0.0][1][f]).all()
