@@ -19,6 +19,7 @@ template <> struct Semiring<GT_PLUS_TIMES_F64> {          // src/apps/pr.h:35-41
     __device__ static __forceinline__ T mul(T x, uint32_t w) { return x * (double) w; }
     __device__ static __forceinline__ bool skip(T) { return false; }
     __device__ static __forceinline__ void reduce(T* y, T v) { atomicAdd(y, v); }     // RED.E.ADD.F64
+    __device__ static __forceinline__ void reduce_dense(T* y, T v) { atomicAdd(y, v); }
     __device__ static __forceinline__ T identity() { return 0.0; }
     __device__ static __forceinline__ T plus(T a, T b) { return a + b; }
 };
@@ -26,9 +27,11 @@ template <> struct Semiring<GT_MIN_PLUS_U32> {            // src/apps/sssp.h:49-
     typedef uint32_t T;
     __device__ static __forceinline__ T mul(T x, uint32_t w) { return x + w; }
     __device__ static __forceinline__ bool skip(T x) { return x == GT_INF_U32; }
-    // y only ever decreases, so a (possibly stale) L2 read that is already <= v proves the RED useless;
-    // hub rows settle after a few updates and stop serialising in L2
-    __device__ static __forceinline__ void reduce(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }     // RED.E.MIN
+    __device__ static __forceinline__ void reduce(T* y, T v) { atomicMin(y, v); }     // RED.E.MIN
+    // Dense passes only: y only ever decreases, so a (possibly stale) L2 read that is already <= v proves the
+    // RED useless; hub rows settle after a few updates and stop serialising in L2 (CC RMAT-24: 12.0 -> 9.1 ms).
+    // Not used by the frontier kernel, where most updates are first visits and the extra read costs 2-3x.
+    __device__ static __forceinline__ void reduce_dense(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }
     __device__ static __forceinline__ T identity() { return GT_INF_U32; }
     __device__ static __forceinline__ T plus(T a, T b) { return a < b ? a : b; }
 };
@@ -36,7 +39,8 @@ template <> struct Semiring<GT_MIN_SELECT_U32> {          // src/apps/bfs.h:61-6
     typedef uint32_t T;
     __device__ static __forceinline__ T mul(T x, uint32_t w) { return x + w; }      // bfs.h:56-59 (weighted build)
     __device__ static __forceinline__ bool skip(T x) { return x == GT_INF_U32; }
-    __device__ static __forceinline__ void reduce(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }
+    __device__ static __forceinline__ void reduce(T* y, T v) { atomicMin(y, v); }
+    __device__ static __forceinline__ void reduce_dense(T* y, T v) { if (v < __ldcg(y)) atomicMin(y, v); }
     __device__ static __forceinline__ T identity() { return GT_INF_U32; }
     __device__ static __forceinline__ T plus(T a, T b) { return a < b ? a : b; }
 };
@@ -140,7 +144,7 @@ k_spmv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, co
                 if (k >= m) break;
                 if (cols[k] != last) { xv = __ldg(x + cols[k]); last = cols[k]; }
                 if (SKIP_INF && SR::skip(xv)) continue;
-                SR::reduce(y + rows[k], WEIGHTED ? SR::mul(xv, wts[k]) : xv);
+                SR::reduce_dense(y + rows[k], WEIGHTED ? SR::mul(xv, wts[k]) : xv);
                 if (t) t[rows[k]] = 1;
             }
         }
