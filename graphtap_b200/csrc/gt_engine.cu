@@ -319,7 +319,9 @@ struct gt_program {
     struct Span { uint8_t* p = nullptr; size_t n = 0; };
     gt::DevBuf<uint8_t> Xcat;                      // all local x segments back to back + one trailing zero element
     std::vector<Span> X;                           // views into Xcat, |x|*esize bytes each
-    std::vector<gt::DevBuf<uint8_t>> Y;            // raw bytes, |y|*esize
+    gt::DevBuf<uint8_t> Ycat;                      // all local y segments, same chunking along the row group
+    std::vector<Span> Y;                           // views into Ycat, |y|*esize bytes each
+    size_t xchunk = 0, ychunk = 0;                 // chunk sizes in elements
     int pr_layout = 1;                             // 1: derived pull layout for the plus-times SpMV (gt_pull.cu), 0: push over TCSC
     const gt::PullLayout* pull = nullptr;          // owned by the graph
     // pull mode: x / y in hot order, and the owned segment's state in hot order while execute() runs
@@ -370,19 +372,32 @@ static void prog_alloc(gt_program* P) {
     P->C.alloc(P->th);
     P->X.resize(P->pcol->size());
     P->Y.resize(P->prow->size());
+    // x: one equal-sized chunk per member of the broadcast group, chunk q = the segment led by group rank q, so the
+    // whole exchange is ONE in-place ncclAllGather (the reference: one Ibcast per segment, :843-862,970-1013); y: the
+    // same along the reduce group with ONE in-place ncclReduceScatter (the reference: Isend to the leader + host-side
+    // combine, :1083-1108,1522-1573).  Every member leads exactly one of its group's segments (tests/test_layout.py).
     {
-        size_t total = 0;
-        for (size_t k = 0; k < P->X.size(); k++) total += (*P->pcol)[k].nnz;
-        P->Xcat.alloc((total + 1) * P->esize());
-        GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, P->ctx->stream));      // x[total] stays 0: the pull layout's padding target
-        size_t off = 0;
+        gt_ctx* ctx = P->ctx;
+        auto chunk_of = [&](CommGroup grp, int segment, size_t k) {
+            return ctx->comm ? (size_t) comm_index_of_world_rank(ctx->comm, grp, g->lay.leader_ranks[segment]) : k;
+        };
+        for (const SegMaps& s : *P->pcol) P->xchunk = std::max<size_t>(P->xchunk, s.nnz);
+        for (const SegMaps& s : *P->prow) P->ychunk = std::max<size_t>(P->ychunk, s.nnz);
+        P->xchunk = (P->xchunk + 3) / 4 * 4;           // chunks stay 16-byte aligned for both element sizes
+        P->ychunk = (P->ychunk + 3) / 4 * 4;
+        P->Xcat.alloc((P->X.size() * P->xchunk + 1) * P->esize());
+        P->Ycat.alloc(std::max<size_t>(1, P->Y.size() * P->ychunk) * P->esize());
+        GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, ctx->stream));
+        GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, ctx->stream));
         for (size_t k = 0; k < P->X.size(); k++) {
-            P->X[k].p = P->Xcat.p + off * P->esize();
+            P->X[k].p = P->Xcat.p + chunk_of(P->bcast_group, (*P->pcol)[k].segment, k) * P->xchunk * P->esize();
             P->X[k].n = (size_t) (*P->pcol)[k].nnz * P->esize();
-            off += (*P->pcol)[k].nnz;
+        }
+        for (size_t k = 0; k < P->Y.size(); k++) {
+            P->Y[k].p = P->Ycat.p + chunk_of(P->reduce_group, (*P->prow)[k].segment, k) * P->ychunk * P->esize();
+            P->Y[k].n = (size_t) (*P->prow)[k].nnz * P->esize();
         }
     }
-    for (size_t k = 0; k < P->Y.size(); k++) P->Y[k].alloc((size_t) (*P->prow)[k].nnz * P->esize());
     if (!P->stationary) {
         P->XI.resize(P->X.size()); P->XV.resize(P->X.size());
         for (size_t k = 0; k < P->X.size(); k++) { P->XI[k].alloc((*P->pcol)[k].nnz); P->XV[k].alloc((*P->pcol)[k].nnz); }
@@ -402,12 +417,9 @@ static void prog_initialize(gt_program* P) {
     k_init_state<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->th, P->vid0, P->prm.root, P->prm.alpha, P->stationary);
     ctx->kernel_launches++;
     if (!P->stationary) {                       // Y starts at infinity() (:625-635)
-        for (size_t k = 0; k < P->Y.size(); k++) {
-            const uint64_t n = (*P->prow)[k].nnz;
-            if (!n) continue;
-            k_fill<uint32_t><<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((uint32_t*) P->Y[k].p, GT_INF_U32, n);
-            ctx->kernel_launches++;
-        }
+        const uint64_t n = P->Ycat.n / 4;
+        k_fill<uint32_t><<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((uint32_t*) P->Ycat.p, GT_INF_U32, n);
+        ctx->kernel_launches++;
     }
     GT_CUDA(cudaGetLastError());
     // PageRank's plus-times SpMV runs as a pull over the derived layout (gt_pull.cu) unless pr_layout = 0
@@ -531,17 +543,9 @@ static void scatter_gather(gt_program* P) {
         else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
         ctx->kernel_launches++;
     }
-    if (ctx->comm) {                              // bcast_stationary / bcast_nonstationary
-        comm_group_start(ctx->comm);
-        for (size_t k = 0; k < P->X.size(); k++) {
-            const SegMaps& s = (*P->pcol)[k];
-            if (!s.nnz) continue;
-            const int root = comm_index_of_world_rank(ctx->comm, P->bcast_group, P->g->lay.leader_ranks[s.segment]);
-            comm_bcast(ctx->comm, P->bcast_group, P->X[k].p, s.nnz, P->f64 ? CT_F64 : CT_U32, root, st);
-        }
-        comm_group_end(ctx->comm);
-    }
-    if (!P->stationary) {                         // frontier lists + sizes (:754-784)
+    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)      // bcast_stationary / bcast_nonstationary
+        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xcat.p, P->xchunk, P->f64 ? CT_F64 : CT_U32, st);
+    if (!P->stationary) {                         // frontier lists + sizes (:754-784); the caller synchronises
         GT_CUDA(cudaMemsetAsync(P->d_counts.p, 0, P->d_counts.bytes(), st));
         for (size_t k = 0; k < P->X.size(); k++) {
             const SegMaps& s = (*P->pcol)[k];
@@ -550,7 +554,6 @@ static void scatter_gather(gt_program* P) {
             ctx->kernel_launches++;
         }
         GT_CUDA(cudaMemcpyAsync(P->h_counts, P->d_counts.p, P->X.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-        GT_CUDA(cudaStreamSynchronize(st));
     }
     GT_CUDA(cudaGetLastError());
 }
@@ -560,9 +563,7 @@ static void combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     gt_graph* g = P->g;
-    if (P->stationary)                            // std::fill(y, 0) (:1026-1032)
-        for (size_t k = 0; k < P->Y.size(); k++)
-            if (P->Y[k].n) GT_CUDA(cudaMemsetAsync(P->Y[k].p, 0, P->Y[k].n, st));
+    if (P->stationary) GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, st));     // std::fill(y, 0) (:1026-1032)
     bool any_sparse = false, all_sparse = !P->stationary;
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
@@ -583,16 +584,8 @@ static void combine(gt_program* P) {
     }
     if (any_sparse) P->tm.sparse_iterations++;
     P->dense_tiles = !all_sparse;
-    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1) {
-        comm_group_start(ctx->comm);
-        for (size_t k = 0; k < P->Y.size(); k++) {
-            const SegMaps& s = (*P->prow)[k];
-            if (!s.nnz) continue;
-            const int root = comm_index_of_world_rank(ctx->comm, P->reduce_group, g->lay.leader_ranks[s.segment]);
-            comm_reduce(ctx->comm, P->reduce_group, P->Y[k].p, P->Y[k].p, s.nnz, P->f64 ? CT_F64 : CT_U32, P->f64 ? CO_SUM : CO_MIN, root, st);
-        }
-        comm_group_end(ctx->comm);
-    }
+    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
+        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Ycat.p, P->ychunk, P->f64 ? CT_F64 : CT_U32, P->f64 ? CO_SUM : CO_MIN, st);
 }
 
 static void apply(gt_program* P, bool count_active = false) {
@@ -615,8 +608,8 @@ static void apply(gt_program* P, bool count_active = false) {
     GT_CUDA(cudaGetLastError());
 }
 
-// all C == 0 on all ranks (:1884-1923)
-static bool has_converged(gt_program* P) {
+// all C == 0 on all ranks (:1884-1923): device count (+ ncclAllReduce), one 8-byte D2H
+static void has_converged_begin(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     if (P->stationary && !P->pull) {
@@ -626,7 +619,9 @@ static bool has_converged(gt_program* P) {
     }
     if (ctx->comm) comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p, P->d_active.p, 1, CT_U64, CO_SUM, st);
     GT_CUDA(cudaMemcpyAsync(P->h_active, P->d_active.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    GT_CUDA(cudaStreamSynchronize(st));
+}
+static bool has_converged_end(gt_program* P) {
+    GT_CUDA(cudaStreamSynchronize(P->ctx->stream));
     return P->h_active[0] == 0;
 }
 
@@ -721,8 +716,16 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
             GT_CUDA(cudaStreamSynchronize(ctx->stream));
             acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         };
+        // Non-stationary programs need two numbers on the host per iteration: the frontier sizes (to pick SpMSpV vs
+        // SpMV per column segment, :1475) and the active count (convergence).  The next iteration's scatter_gather is
+        // enqueued BEFORE waiting for the active count, so both arrive with a single stream synchronisation.
+        bool sg_done = false;
         while (true) {
-            phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
+            if (!sg_done) {
+                phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
+                if (!p->stationary) GT_CUDA(cudaStreamSynchronize(ctx->stream));      // h_counts
+            }
+            sg_done = false;
             p->sparse_bytes = 0; p->dense_tiles = true;
             phase(p->tm.combine_ms, [&] { gt::combine(p); });
             phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
@@ -731,7 +734,9 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
             // frontier branch is counted at its lower bound (xi/xv + JA pairs of the k frontier columns)
             p->tm.bytes_algorithmic += p->dense_tiles ? dense_bytes : p->sparse_bytes;
             if (check) {
-                p->converged = gt::has_converged(p);
+                gt::has_converged_begin(p);
+                if (!p->stationary && !p->timing) { gt::scatter_gather(p); sg_done = true; }   // overlaps the wait below
+                p->converged = gt::has_converged_end(p);
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
             } else if (p->iteration >= num_iterations) break;
         }
@@ -753,7 +758,7 @@ extern "C" int gt_program_run_phase(gt_program* p, int phase) {
         GT_REQUIRE(phase >= 0 && phase <= 2, "gt_program_run_phase: phase must be 0, 1 or 2");
         GT_CUDA(cudaSetDevice(p->ctx->device));
         if (p->pull) gt::pull_state_in(p);
-        if (phase == 0) { p->x_ready = false; gt::scatter_gather(p); }
+        if (phase == 0) { p->x_ready = false; gt::scatter_gather(p); GT_CUDA(cudaStreamSynchronize(p->ctx->stream)); }
         else if (phase == 1) gt::combine(p);
         else gt::apply(p);
     });

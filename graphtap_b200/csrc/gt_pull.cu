@@ -42,12 +42,12 @@ static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) 
 __global__ void k_compose(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ pos, uint32_t add, uint32_t* __restrict__ out) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[j] = add + pos[ids[j]];
 }
-// optional shared-memory hot cache: positions < hot_per_seg of column slot `slot` become smem slots
-__global__ void k_col_codes(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ pos, uint32_t slot, uint32_t hot_per_seg,
-                            uint32_t hot_total, uint32_t xoff, uint32_t* __restrict__ code) {
+// column code of a compressed column: index into the concatenated x, | kPullHotBit for the segment's hottest
+__global__ void k_col_codes(const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ pos, uint32_t l1hot, uint32_t xoff,
+                            uint32_t* __restrict__ code) {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const uint32_t r = pos[ids[j]];
-        code[j] = r < hot_per_seg ? slot * hot_per_seg + r : hot_total + xoff + r;
+        code[j] = (xoff + r) | (r < l1hot ? kPullHotBit : 0u);
     }
 }
 // one (row', colcode) key per stored entry of a tile
@@ -138,22 +138,50 @@ __global__ void k_count_nonzero_slices(const uint64_t* __restrict__ slice_ptr, u
 // same mix of long and short ones).  Inner loop, per lane: 8 independent 4-byte index loads (streaming,
 // coalesced across the warp), 8 independent gathers (shared memory for hot codes, read-only global for the
 // rest), 8 adds.  One coalesced store of y per slice; virtual rows of split rows use RED.ADD.
-template <int UNROLL>
+// Column code = index into the concatenated x | kPullHotBit when the column is among the `l1hot` hottest of its
+// segment.  Hot gathers use allocating loads (they are re-read by every warp of the SM, so L1 keeps them), cold
+// gathers use L1::no_allocate so that they do not evict the hot lines.  With L2HINT the index stream is read
+// evict-first and x evict-last in L2, so the 4 B/edge stream does not push x out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+template <bool L2HINT>
+__device__ __forceinline__ uint32_t ld_index(const uint32_t* p, uint64_t pol) {
+    uint32_t r;
+    if (L2HINT) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <bool L1SPLIT, bool L2HINT>
+__device__ __forceinline__ double ld_x(const double* __restrict__ x, uint32_t code, uint64_t pol) {
+    double v;
+    const double* p = x + (code & ~kPullHotBit);
+    if (!L1SPLIT) {
+        if (L2HINT) asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        else v = __ldg(p);
+    } else if (code & kPullHotBit) {       // hot: keep in L1 as long as possible
+        if (L2HINT) asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        else asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    } else {                               // cold: still allocates (L1 lines track the misses in flight; no_allocate
+                                           // gathers were 1.5x slower, profiles/r01_sweep_pull_cachepolicy_s26.log) but leaves first
+        if (L2HINT) asm volatile("ld.global.nc.L1::evict_first.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        else asm volatile("ld.global.nc.L1::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    }
+    return v;
+}
+
+// Persistent CTAs.  Each warp takes slices round-robin; slices are sorted by decreasing length and dealt to
+// consecutive CTAs (not to consecutive warps of one CTA), so every SM receives the same mix of long and short
+// slices: with the naive order the longest slices all landed on the first few SMs and the rest of the chip idled
+// (profiles/r01_ncu_pull_v0_s22.txt).  Inner loop, per lane: UNROLL independent 4-byte index loads (coalesced
+// across the warp), UNROLL independent 8-byte gathers, UNROLL adds.  One store of y per virtual row; virtual rows
+// of split rows use RED.ADD.
+template <int UNROLL, bool L1SPLIT, bool L2HINT>
 __global__ void __launch_bounds__(kPullThreads)
 k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
-                 const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, PullHot hot, double* __restrict__ y) {
-    extern __shared__ double xs[];
-    for (uint32_t i = threadIdx.x; i < hot.total; i += blockDim.x) {     // hot.total == 0 when the cache is disabled
-        const uint32_t s = i / hot.per_seg, k = i - s * hot.per_seg;
-        xs[i] = k < hot.seg_len[s] ? x[hot.xoff[s] + k] : 0.0;
-    }
-    __syncthreads();
+                 const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, double* __restrict__ y) {
     const int lane = threadIdx.x & 31;
-    // Slices are sorted by decreasing length.  Consecutive slices go to consecutive CTAs (not to consecutive
-    // warps of one CTA), so every SM receives the same mix of long and short slices: with the naive order the
-    // longest slices all landed on the first few SMs and the rest of the chip idled (profiles/r01_ncu_pull_v0).
     const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarps = gridDim.x * (blockDim.x >> 5);
-    const double* xc = x - hot.total;                   // code - hot.total indexes x
+    const uint64_t pol_idx = L2HINT ? l2_policy_evict_first() : 0, pol_x = L2HINT ? l2_policy_evict_last() : 0;
     for (uint32_t s = warp; s < nslices; s += nwarps) {
         const uint64_t base = slice_ptr[s];
         const uint32_t L = (uint32_t) ((slice_ptr[s + 1] - base) >> 5);
@@ -163,17 +191,14 @@ k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__
         for (; k + UNROLL <= L; k += UNROLL) {
             uint32_t c[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) c[u] = ld_stream_u32(p + (uint64_t) (k + u) * 32);
+            for (int u = 0; u < UNROLL; u++) c[u] = ld_index<L2HINT>(p + (uint64_t) (k + u) * 32, pol_idx);
             double v[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; u++) v[u] = c[u] < hot.total ? xs[c[u]] : __ldg(xc + c[u]);
+            for (int u = 0; u < UNROLL; u++) v[u] = ld_x<L1SPLIT, L2HINT>(x, c[u], pol_x);
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) acc += v[u];
         }
-        for (; k < L; k++) {
-            const uint32_t c = ld_stream_u32(p + (uint64_t) k * 32);
-            acc += c < hot.total ? xs[c] : __ldg(xc + c);
-        }
+        for (; k < L; k++) acc += ld_x<L1SPLIT, L2HINT>(x, ld_index<L2HINT>(p + (uint64_t) k * 32, pol_idx), pol_x);
         const uint32_t v = s * 32 + lane;
         if (v < nv) {
             const uint32_t t = vtgt[v];
@@ -192,7 +217,9 @@ PullLayout* pull_build(gt_graph* g) {
     const size_t S = g->cols.size(), R = g->rows.size();
     GT_REQUIRE(S <= kPullMaxSegs, "pull layout: too many local column segments");
     if (const char* e = getenv("GT_PULL_VROW")) P->vrow = std::max(8, atoi(e));
-    if (const char* e = getenv("GT_PULL_HOT")) P->hot_doubles = std::min(28000, std::max(0, atoi(e)));
+    if (const char* e = getenv("GT_PULL_L1HOT")) P->l1hot = (uint32_t) std::max(0, atoi(e));
+    if (const char* e = getenv("GT_PULL_L2HINT")) P->l2hint = atoi(e) != 0;
+    if (const char* e = getenv("GT_PULL_UNROLL")) P->unroll = atoi(e) == 4 ? 4 : 8;
     if (const char* e = getenv("GT_PULL_THREADS")) P->threads = std::min(1024, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GT_PULL_CTAS")) P->ctas_per_sm = std::min(8, std::max(1, atoi(e)));
     const uint32_t kVRow = P->vrow;
@@ -211,13 +238,10 @@ PullLayout* pull_build(gt_graph* g) {
         const int q = ctx->comm ? comm_index_of_world_rank(ctx->comm, COMM_ROWGRP, g->lay.leader_ranks[g->rows[k].segment]) : (int) k;
         P->yoff[k] = (uint32_t) q * P->ychunk;
     }
-    GT_REQUIRE((uint64_t) S * P->xchunk + P->hot_doubles + 2 < (1ull << 32), "pull layout: x space exceeds 32-bit codes");
+    GT_REQUIRE((uint64_t) S * P->xchunk + 2 < (1ull << 31), "pull layout: x space exceeds 31-bit codes");
     P->xlen = (uint32_t) S * P->xchunk;
     P->ylen = (uint32_t) R * P->ychunk;
-    P->hot.per_seg = (uint32_t) (P->hot_doubles / S);
-    P->hot.total = P->hot.per_seg * (uint32_t) S;
-    for (size_t k = 0; k < kPullMaxSegs; k++) { P->hot.xoff[k] = k < S ? P->xoff[k] : 0; P->hot.seg_len[k] = k < S ? P->xn[k] : 0; }
-    const uint32_t pad_code = P->hot.total + P->xlen;         // x[xlen] is a permanent 0.0
+    const uint32_t pad_code = P->xlen;                         // x[xlen] is a permanent 0.0
 
     // 1. compressed column id -> code, compressed row id -> y index
     std::vector<DevBuf<uint32_t>> col_code(S), row_rank(R);
@@ -225,8 +249,8 @@ PullLayout* pull_build(gt_graph* g) {
         const uint32_t n = g->cols[k].nnz;
         col_code[k].alloc(n);
         if (n) {
-            k_col_codes<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(g->cols[k].ids.p, n, g->hot[g->hot_of_col_slot[k]].pos.p, (uint32_t) k,
-                                                                       P->hot.per_seg, P->hot.total, P->xoff[k], col_code[k].p);
+            k_col_codes<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(g->cols[k].ids.p, n, g->hot[g->hot_of_col_slot[k]].pos.p,
+                                                                       P->l1hot / (uint32_t) S, P->xoff[k], col_code[k].p);
             ctx->kernel_launches++;
         }
     }
@@ -243,8 +267,7 @@ PullLayout* pull_build(gt_graph* g) {
     GT_CUDA(cudaGetLastError());
 
     // 2. per row slot: expand -> sort by (row', code) -> virtual rows -> SELL-32
-    int code_bits = 1;
-    while (code_bits < 32 && (1ull << code_bits) <= (uint64_t) pad_code) code_bits++;
+    const int code_bits = 32;                                  // bit 31 carries the hot flag
     for (size_t k = 0; k < R; k++) {
         PullRows& Q = P->rows[k];
         const uint32_t nr = Q.ny;          // rows are addressed by y index (position in the segment's hot order)
@@ -344,7 +367,6 @@ PullLayout* pull_build(gt_graph* g) {
         GT_CUDA(cudaGetLastError());
         GT_CUDA(cudaStreamSynchronize(st));
     }
-    GT_CUDA(cudaFuncSetAttribute(k_spmv_pull_sell<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (28000 * sizeof(double))));
     return P.release();
 }
 
@@ -354,8 +376,17 @@ void pull_free(PullLayout* P) { delete P; }
 void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, const double* x, double* y) {
     const PullRows& Q = P->rows[row_slot];
     if (!Q.nslices) return;
-    k_spmv_pull_sell<8><<<ctx->sm_count * P->ctas_per_sm, P->threads, P->hot.total * sizeof(double), ctx->stream>>>(
-        Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, P->hot, y);
+    const int grid = ctx->sm_count * P->ctas_per_sm;
+#define GT_PULL_LAUNCH(U, A, B) k_spmv_pull_sell<U, A, B><<<grid, P->threads, 0, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, y)
+    const bool split = P->l1hot > 0;
+    if (P->unroll == 4) {
+        if (split) { if (P->l2hint) GT_PULL_LAUNCH(4, true, true); else GT_PULL_LAUNCH(4, true, false); }
+        else { if (P->l2hint) GT_PULL_LAUNCH(4, false, true); else GT_PULL_LAUNCH(4, false, false); }
+    } else {
+        if (split) { if (P->l2hint) GT_PULL_LAUNCH(8, true, true); else GT_PULL_LAUNCH(8, true, false); }
+        else { if (P->l2hint) GT_PULL_LAUNCH(8, false, true); else GT_PULL_LAUNCH(8, false, false); }
+    }
+#undef GT_PULL_LAUNCH
     ctx->kernel_launches++;
     GT_CUDA(cudaGetLastError());
 }

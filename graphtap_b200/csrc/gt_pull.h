@@ -7,13 +7,8 @@ namespace gt {
 constexpr uint32_t kPullMaxSegs = 8;            // local column segments per rank (rank_ncolgrps: 1,2,2,4 at p = 1,2,4,8)
 constexpr uint32_t kPullVRow = 512;             // longest run of entries one lane sums before the row is split (GT_PULL_VROW)
 constexpr uint32_t kPullSplit = 0x80000000u;    // vtgt flag: partial sum of a split row -> RED.ADD
+constexpr uint32_t kPullHotBit = 0x80000000u;   // column-code flag: one of the hottest columns -> L1-allocating gather
 constexpr int kPullThreads = 1024;
-
-struct PullHot {                                // optional shared-memory copy of the hottest x values (off by default)
-    uint32_t total, per_seg;
-    uint32_t xoff[kPullMaxSegs];                // start of segment s in the concatenated x buffer
-    uint32_t seg_len[kPullMaxSegs];
-};
 
 struct PullRows {                               // one local row segment
     uint32_t ny = 0;                            // length of its y vector = vertices in the segment's hot order
@@ -32,10 +27,11 @@ struct PullLayout {
     uint32_t xchunk = 0, xlen = 0;              // chunk size, total; x[xlen] is a permanent 0.0 (padding target)
     std::vector<uint32_t> yoff, yn;             // per row slot
     uint32_t ychunk = 0, ylen = 0;
-    PullHot hot{};
     std::vector<PullRows> rows;                 // per row slot
     uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
-    uint32_t hot_doubles = 0;
+    uint32_t l1hot = 0;                         // hottest columns (per rank) gathered L1::evict_last, the rest L1::evict_first; 0 = no distinction
+    bool l2hint = true;                         // L2 eviction hints: index stream evict-first, x evict-last (-8 % on RMAT-26)
+    int unroll = 8;
     int threads = kPullThreads, ctas_per_sm = 2;
 };
 
