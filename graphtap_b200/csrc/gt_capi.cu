@@ -38,6 +38,9 @@ extern "C" int gt_ctx_create(int device, int rank, int nranks, const void* nccl_
         c->device = device; c->rank = rank; c->nranks = nranks;
         c->sm_count = prop.multiProcessorCount;
         GT_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        GT_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+        GT_CUDA(cudaEventCreateWithFlags(&c->ev_x, cudaEventDisableTiming));
+        GT_CUDA(cudaEventCreateWithFlags(&c->ev_ag, cudaEventDisableTiming));
         if (nranks > 1) {
             // the communicators depend only on (nranks, rank): the group lists are the same for every
             // graph size (src/mat/matrix.hpp:382-465), so any nvertices gives the same lists
@@ -53,8 +56,11 @@ extern "C" int gt_ctx_destroy(gt_ctx* ctx) {
         if (!ctx) return;
         cudaSetDevice(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
         gt::comm_destroy(ctx->comm);
         if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+        if (ctx->ev_x) { cudaEventDestroy(ctx->ev_x); cudaEventDestroy(ctx->ev_ag); }
+        if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -85,6 +91,7 @@ extern "C" int gt_ctx_sync(gt_ctx* ctx) {
         GT_REQUIRE(ctx, "gt_ctx_sync: NULL ctx");
         GT_CUDA(cudaSetDevice(ctx->device));
         GT_CUDA(cudaStreamSynchronize(ctx->stream));
+        GT_CUDA(cudaStreamSynchronize(ctx->comm_stream));
     });
 }
 

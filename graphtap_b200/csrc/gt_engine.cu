@@ -332,7 +332,7 @@ struct gt_program {
     gt::DevBuf<uint8_t> flag_h, C_h;
     const gt::HotOrder* own_hot = nullptr;
     gt::DevBuf<uint32_t> stage;                    // AoS staging of V for gt_program_state_{to,from}_host (kept: no malloc per call)
-    bool hot_valid = false, x_ready = false;
+    bool hot_valid = false, x_ready = false, ag_pending = false;
     uint64_t sparse_bytes = 0;                     // bytes_algorithmic bookkeeping of the current iteration
     bool dense_tiles = true;
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
@@ -503,8 +503,15 @@ static void pull_scatter_gather(gt_program* P) {
         ctx->kernel_launches++;
     }
     P->x_ready = true;
-    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)       // every member leads exactly one of the group's segments
-        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xh.p, P->pull->xchunk, CT_F64, st);
+    P->ag_pending = false;
+    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
+        // the all-gather runs on its own stream; the SpMV over the own chunk does not wait for it
+        GT_CUDA(cudaEventRecord(ctx->ev_x, st));
+        GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x, 0));
+        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xh.p, P->pull->xchunk, CT_F64, ctx->comm_stream);
+        GT_CUDA(cudaEventRecord(ctx->ev_ag, ctx->comm_stream));
+        P->ag_pending = true;
+    }
     GT_CUDA(cudaGetLastError());
 }
 
@@ -512,8 +519,11 @@ static void pull_combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     if (P->Yh.n) GT_CUDA(cudaMemsetAsync(P->Yh.p, 0, P->Yh.bytes(), st));     // std::fill(y, 0) (:1026-1032)
+    for (size_t k = 0; k < P->pull->rows.size(); k++)                          // needs only this rank's own x chunk
+        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, 0, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
+    if (P->ag_pending) { GT_CUDA(cudaStreamWaitEvent(st, ctx->ev_ag, 0)); P->ag_pending = false; }
     for (size_t k = 0; k < P->pull->rows.size(); k++)
-        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
+        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, 1, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
     if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
         comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, P->pull->ychunk, CT_F64, CO_SUM, st);
 }
@@ -740,6 +750,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
             } else if (p->iteration >= num_iterations) break;
         }
+        if (p->ag_pending) { GT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ag, 0)); p->ag_pending = false; }
         if (p->pull) gt::pull_state_out(p);            // hot-order working state -> V (one pass per execute, inside the timed window)
         GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
         GT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -758,7 +769,12 @@ extern "C" int gt_program_run_phase(gt_program* p, int phase) {
         GT_REQUIRE(phase >= 0 && phase <= 2, "gt_program_run_phase: phase must be 0, 1 or 2");
         GT_CUDA(cudaSetDevice(p->ctx->device));
         if (p->pull) gt::pull_state_in(p);
-        if (phase == 0) { p->x_ready = false; gt::scatter_gather(p); GT_CUDA(cudaStreamSynchronize(p->ctx->stream)); }
+        if (phase == 0) {
+            p->x_ready = false;
+            gt::scatter_gather(p);
+            if (p->ag_pending) { GT_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ctx->ev_ag, 0)); p->ag_pending = false; }
+            GT_CUDA(cudaStreamSynchronize(p->ctx->stream));
+        }
         else if (phase == 1) gt::combine(p);
         else gt::apply(p);
     });

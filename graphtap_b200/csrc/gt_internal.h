@@ -131,4 +131,6 @@ struct gt_ctx {
     int sm_count = 0;
     uint64_t kernel_launches = 0;     // every launch this library makes increments this
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // gt_ctx_timer_*
+    cudaStream_t comm_stream = nullptr;         // collectives that overlap compute (x all-gather of the pull path)
+    cudaEvent_t ev_x = nullptr, ev_ag = nullptr; // own x chunk written / all-gather landed
 };

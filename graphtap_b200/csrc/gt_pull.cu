@@ -175,7 +175,7 @@ __device__ __forceinline__ double ld_x(const double* __restrict__ x, uint32_t co
 // (profiles/r01_ncu_pull_v0_s22.txt).  Inner loop, per lane: UNROLL independent 4-byte index loads (coalesced
 // across the warp), UNROLL independent 8-byte gathers, UNROLL adds.  One store of y per virtual row; virtual rows
 // of split rows use RED.ADD.
-template <int UNROLL, bool L1SPLIT, bool L2HINT>
+template <int UNROLL, bool L1SPLIT, bool L2HINT, bool ACCUM>
 __global__ void __launch_bounds__(kPullThreads)
 k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
                  const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, double* __restrict__ y) {
@@ -203,12 +203,95 @@ k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__
         if (v < nv) {
             const uint32_t t = vtgt[v];
             if (t & kPullSplit) atomicAdd(y + (t & ~kPullSplit), acc);
+            else if (ACCUM) y[t] += acc;              // second pass: a row's owner lane is unique within a pass
             else y[t] = acc;
         }
     }
 }
 
+struct CodeInRange {                            // column code (hot flag masked) inside [lo, hi)
+    uint32_t lo, hi; bool want;
+    __device__ bool operator()(const uint64_t& k) const {
+        const uint32_t c = (uint32_t) k & ~kPullHotBit;
+        return (c >= lo && c < hi) == want;
+    }
+};
+
 // ---- build ---------------------------------------------------------------------------------------------------
+// (row', code)-sorted keys of one row segment -> virtual rows (<= vrow entries) sorted by decreasing length -> SELL-32
+static void build_sell(gt_ctx* ctx, const uint64_t* sorted, uint64_t total, uint32_t nr, uint32_t kVRow, uint32_t pad_code, PullSell& Q) {
+    cudaStream_t st = ctx->stream;
+    Q.nnz = total;
+    if (!total || !nr) return;
+    {
+        DevBuf<uint64_t> rowptr; rowptr.alloc((size_t) nr + 1);
+        k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, total, nr, rowptr.p);
+        // virtual rows
+        DevBuf<uint32_t> nvr; nvr.alloc((size_t) nr + 1);
+        GT_CUDA(cudaMemsetAsync(nvr.p + nr, 0, 4, st));
+        k_vrow_counts<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, nr, kVRow, nvr.p);
+        DevBuf<uint32_t> vbase; vbase.alloc((size_t) nr + 1);
+        {
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        uint32_t nv = 0;
+        GT_CUDA(cudaMemcpyAsync(&nv, vbase.p + nr, 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        Q.nv = nv;
+        DevBuf<uint32_t> vkey, vkey_alt, vid, vid_alt;
+        vkey.alloc(nv); vkey_alt.alloc(nv); vid.alloc(nv); vid_alt.alloc(nv);
+        k_vrow_make<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vkey.p, vid.p);
+        uint32_t* vid_sorted = nullptr;
+        {
+            int lb = 1;
+            while ((1u << lb) <= kVRow) lb++;
+            cub::DoubleBuffer<uint32_t> dk(vkey.p, vkey_alt.p), dv(vid.p, vid_alt.p);
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t) nv, 0, lb, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t) nv, 0, lb, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            vid_sorted = dv.Current();
+        }
+        DevBuf<uint32_t> vpos; vpos.alloc(nv);          // unsorted virtual row -> sorted position
+        k_invert<<<grid_for(nv, 256, ctx->sm_count), 256, 0, st>>>(vid_sorted, nv, vpos.p);
+        DevBuf<uint64_t> vstart; vstart.alloc(nv);
+        DevBuf<uint32_t> vl; vl.alloc(nv);
+        Q.vtgt.alloc(nv);
+        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
+        const uint32_t nslices = (nv + 31) / 32;
+        DevBuf<uint64_t> sizes; sizes.alloc((size_t) nslices + 1);
+        Q.slice_ptr.alloc((size_t) nslices + 1);
+        k_slice_sizes<<<grid_for((uint64_t) nslices + 1, 256, ctx->sm_count), 256, 0, st>>>(vl.p, nv, nslices, sizes.p);
+        {
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        uint64_t sell_len = 0;
+        GT_CUDA(cudaMemcpyAsync(&sell_len, Q.slice_ptr.p + nslices, 8, cudaMemcpyDeviceToHost, st));
+        DevBuf<unsigned int> cnt; cnt.alloc(1);
+        GT_CUDA(cudaMemsetAsync(cnt.p, 0, 4, st));
+        k_count_nonzero_slices<<<grid_for(nslices, 256, ctx->sm_count), 256, 0, st>>>(Q.slice_ptr.p, nslices, cnt.p);
+        unsigned int active = 0;
+        GT_CUDA(cudaMemcpyAsync(&active, cnt.p, 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        Q.nslices = active;
+        Q.sell_len = sell_len;
+        Q.sell.alloc(sell_len);
+        k_sell_fill<<<grid_for((uint64_t) nslices * 32, 256, ctx->sm_count, 8), 256, 0, st>>>(sorted, vstart.p, vl.p, nv, Q.slice_ptr.p, active, pad_code, Q.sell.p);
+        ctx->kernel_launches += 12;
+        GT_CUDA(cudaGetLastError());
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
+}
+
 PullLayout* pull_build(gt_graph* g) {
     gt_ctx* ctx = g->ctx;
     cudaStream_t st = ctx->stream;
@@ -301,71 +384,27 @@ PullLayout* pull_build(gt_graph* g) {
             ctx->kernel_launches += 8;
             sorted = db.Current();
         }
-        DevBuf<uint64_t> rowptr; rowptr.alloc((size_t) nr + 1);
-        k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, total, nr, rowptr.p);
-        // virtual rows
-        DevBuf<uint32_t> nvr; nvr.alloc((size_t) nr + 1);
-        GT_CUDA(cudaMemsetAsync(nvr.p + nr, 0, 4, st));
-        k_vrow_counts<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, nr, kVRow, nvr.p);
-        DevBuf<uint32_t> vbase; vbase.alloc((size_t) nr + 1);
-        {
+        // own x chunk apart from the rest (multi-GPU only)
+        uint64_t* other = (sorted == keys.p) ? alt.p : keys.p;
+        uint64_t n_own = 0;
+        if (ctx->comm && comm_size_in(ctx->comm, COMM_COLGRP) > 1) {
+            const uint32_t lo = P->xoff[g->lay.info.accu_segment_col], hi = lo + P->xchunk;
+            DevBuf<unsigned long long> d_n; d_n.alloc(2);
             size_t tb = 0;
-            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) total, CodeInRange{lo, hi, true}, st));
             DevBuf<uint8_t> tmp; tmp.alloc(tb);
-            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, nvr.p, vbase.p, (int64_t) nr + 1, st));
+            GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) total, CodeInRange{lo, hi, true}, st));
+            unsigned long long h_n = 0;
+            GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
             GT_CUDA(cudaStreamSynchronize(st));
-        }
-        uint32_t nv = 0;
-        GT_CUDA(cudaMemcpyAsync(&nv, vbase.p + nr, 4, cudaMemcpyDeviceToHost, st));
-        GT_CUDA(cudaStreamSynchronize(st));
-        Q.nv = nv;
-        DevBuf<uint32_t> vkey, vkey_alt, vid, vid_alt;
-        vkey.alloc(nv); vkey_alt.alloc(nv); vid.alloc(nv); vid_alt.alloc(nv);
-        k_vrow_make<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vkey.p, vid.p);
-        uint32_t* vid_sorted = nullptr;
-        {
-            int lb = 1;
-            while ((1u << lb) <= kVRow) lb++;
-            cub::DoubleBuffer<uint32_t> dk(vkey.p, vkey_alt.p), dv(vid.p, vid_alt.p);
-            size_t tb = 0;
-            GT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int64_t) nv, 0, lb, st));
-            DevBuf<uint8_t> tmp; tmp.alloc(tb);
-            GT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int64_t) nv, 0, lb, st));
+            n_own = h_n;
+            GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) total, CodeInRange{lo, hi, false}, st));
             GT_CUDA(cudaStreamSynchronize(st));
-            vid_sorted = dv.Current();
+            ctx->kernel_launches += 2;
+            sorted = other;
         }
-        DevBuf<uint32_t> vpos; vpos.alloc(nv);          // unsorted virtual row -> sorted position
-        k_invert<<<grid_for(nv, 256, ctx->sm_count), 256, 0, st>>>(vid_sorted, nv, vpos.p);
-        DevBuf<uint64_t> vstart; vstart.alloc(nv);
-        DevBuf<uint32_t> vl; vl.alloc(nv);
-        Q.vtgt.alloc(nv);
-        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
-        const uint32_t nslices = (nv + 31) / 32;
-        DevBuf<uint64_t> sizes; sizes.alloc((size_t) nslices + 1);
-        Q.slice_ptr.alloc((size_t) nslices + 1);
-        k_slice_sizes<<<grid_for((uint64_t) nslices + 1, 256, ctx->sm_count), 256, 0, st>>>(vl.p, nv, nslices, sizes.p);
-        {
-            size_t tb = 0;
-            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
-            DevBuf<uint8_t> tmp; tmp.alloc(tb);
-            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, sizes.p, Q.slice_ptr.p, (int64_t) nslices + 1, st));
-            GT_CUDA(cudaStreamSynchronize(st));
-        }
-        uint64_t sell_len = 0;
-        GT_CUDA(cudaMemcpyAsync(&sell_len, Q.slice_ptr.p + nslices, 8, cudaMemcpyDeviceToHost, st));
-        DevBuf<unsigned int> cnt; cnt.alloc(1);
-        GT_CUDA(cudaMemsetAsync(cnt.p, 0, 4, st));
-        k_count_nonzero_slices<<<grid_for(nslices, 256, ctx->sm_count), 256, 0, st>>>(Q.slice_ptr.p, nslices, cnt.p);
-        unsigned int active = 0;
-        GT_CUDA(cudaMemcpyAsync(&active, cnt.p, 4, cudaMemcpyDeviceToHost, st));
-        GT_CUDA(cudaStreamSynchronize(st));
-        Q.nslices = active;
-        Q.sell_len = sell_len;
-        Q.sell.alloc(sell_len);
-        k_sell_fill<<<grid_for((uint64_t) nslices * 32, 256, ctx->sm_count, 8), 256, 0, st>>>(sorted, vstart.p, vl.p, nv, Q.slice_ptr.p, active, pad_code, Q.sell.p);
-        ctx->kernel_launches += 12;
-        GT_CUDA(cudaGetLastError());
-        GT_CUDA(cudaStreamSynchronize(st));
+        if (n_own) build_sell(ctx, sorted, n_own, nr, kVRow, pad_code, Q.own);
+        build_sell(ctx, sorted + n_own, total - n_own, nr, kVRow, pad_code, Q.rest);
     }
     return P.release();
 }
@@ -373,19 +412,24 @@ PullLayout* pull_build(gt_graph* g) {
 void pull_free(PullLayout* P) { delete P; }
 
 // y[row slot] = sum over the slot's rows; x = the concatenated, hot-ordered x buffer (x[xlen] == 0.0)
-void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, const double* x, double* y) {
-    const PullRows& Q = P->rows[row_slot];
+// x = the concatenated, hot-ordered x buffer (x[xlen] == 0.0); y zero-filled by the caller
+void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, const double* x, double* y) {
+    const PullRows& R = P->rows[row_slot];
+    const PullSell& Q = part == 0 ? R.own : R.rest;
+    const bool accum = part == 1 && R.own.nslices > 0;
     if (!Q.nslices) return;
     const int grid = ctx->sm_count * P->ctas_per_sm;
-#define GT_PULL_LAUNCH(U, A, B) k_spmv_pull_sell<U, A, B><<<grid, P->threads, 0, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, y)
+#define GT_PULL_LAUNCH(U, A, B, C) k_spmv_pull_sell<U, A, B, C><<<grid, P->threads, 0, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, y)
+#define GT_PULL_AB(U, A, B) do { if (accum) GT_PULL_LAUNCH(U, A, B, true); else GT_PULL_LAUNCH(U, A, B, false); } while (0)
     const bool split = P->l1hot > 0;
     if (P->unroll == 4) {
-        if (split) { if (P->l2hint) GT_PULL_LAUNCH(4, true, true); else GT_PULL_LAUNCH(4, true, false); }
-        else { if (P->l2hint) GT_PULL_LAUNCH(4, false, true); else GT_PULL_LAUNCH(4, false, false); }
+        if (split) { if (P->l2hint) GT_PULL_AB(4, true, true); else GT_PULL_AB(4, true, false); }
+        else { if (P->l2hint) GT_PULL_AB(4, false, true); else GT_PULL_AB(4, false, false); }
     } else {
-        if (split) { if (P->l2hint) GT_PULL_LAUNCH(8, true, true); else GT_PULL_LAUNCH(8, true, false); }
-        else { if (P->l2hint) GT_PULL_LAUNCH(8, false, true); else GT_PULL_LAUNCH(8, false, false); }
+        if (split) { if (P->l2hint) GT_PULL_AB(8, true, true); else GT_PULL_AB(8, true, false); }
+        else { if (P->l2hint) GT_PULL_AB(8, false, true); else GT_PULL_AB(8, false, false); }
     }
+#undef GT_PULL_AB
 #undef GT_PULL_LAUNCH
     ctx->kernel_launches++;
     GT_CUDA(cudaGetLastError());

@@ -10,13 +10,20 @@ constexpr uint32_t kPullSplit = 0x80000000u;    // vtgt flag: partial sum of a s
 constexpr uint32_t kPullHotBit = 0x80000000u;   // column-code flag: one of the hottest columns -> L1-allocating gather
 constexpr int kPullThreads = 1024;
 
-struct PullRows {                               // one local row segment
-    uint32_t ny = 0;                            // length of its y vector = vertices in the segment's hot order
+struct PullSell {                               // one SELL-32 array
     uint32_t nv = 0, nslices = 0;
     uint64_t nnz = 0, sell_len = 0;
-    DevBuf<uint32_t> sell;                      // SELL-32 column codes, slice-major then column-major
+    DevBuf<uint32_t> sell;                      // column codes, slice-major then column-major
     DevBuf<uint64_t> slice_ptr;                 // [nslices_all + 1]
     DevBuf<uint32_t> vtgt;                      // [nv] y index (| kPullSplit)
+};
+
+struct PullRows {                               // one local row segment
+    uint32_t ny = 0;                            // length of its y vector = vertices in the segment's hot order
+    uint64_t nnz = 0;
+    // Multi-GPU: entries whose column lies in this rank's OWN x chunk are kept apart, so that part of the SpMV can
+    // run while the all-gather of the other chunks is still in flight.  Single GPU: `own` is empty.
+    PullSell own, rest;
 };
 
 struct PullLayout {
@@ -37,6 +44,7 @@ struct PullLayout {
 
 PullLayout* pull_build(gt_graph* g);
 void pull_free(PullLayout* P);
-void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, const double* x, double* y);
+// part 0: the rank's own x chunk (y = ...), part 1: everything else (y += ... when part 0 exists)
+void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, const double* x, double* y);
 
 }  // namespace gt
