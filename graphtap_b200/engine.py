@@ -95,6 +95,43 @@ class Env:
             print(f"{preamble} time: {seconds:f} seconds")
 
 
+def _looks_like_text(path: str) -> bool:
+    with open(path, "rb") as f:
+        head = f.read(4096)
+    return len(head) > 0 and all(b in b"0123456789 \t\r\n#%.-+eE" or 32 <= b < 127 for b in head) and b"\x00" not in head
+
+
+def read_edge_list(path: str, weighted: bool) -> np.ndarray:
+    """Host-side reader of the reference's two input formats, returning (n, 2|3) uint32 records.
+
+    binary: headless array of ``{u32 row, u32 col[, u32 weight]}`` (``src/mat/graph.hpp:307-372``);
+    text:   leading lines starting with '#' or '%' (or empty) are skipped, then one ``row col[ weight]`` per line,
+            single-space separated, up to the first empty line (``src/mat/graph.hpp:194-304``); a line with the wrong
+            number of fields is the reference's ``read() failure`` error."""
+    rec = 3 if weighted else 2
+    if not _looks_like_text(path):
+        data = np.fromfile(path, dtype="<u4")
+        if data.size % rec:
+            raise capi.GraphTapError(capi.GT_ERR_INVALID, f"{path}: size is not a multiple of the {rec * 4}-byte record")
+        return data.reshape(-1, rec)
+    rows = []
+    with open(path, "r") as f:
+        started = False
+        for line in f:
+            line = line.rstrip("\n").rstrip("\r")
+            if not started:
+                if line == "" or line[0] in "#%":
+                    continue
+                started = True
+            if line == "":
+                break
+            fields = line.split(" ")
+            if len(fields) != rec:
+                raise capi.GraphTapError(capi.GT_ERR_INVALID, f'read() failure "{line}"')
+            rows.append([int(x) for x in fields])
+    return np.asarray(rows, dtype="<u4").reshape(-1, rec)
+
+
 class Graph:
     """``Graph<Weight, Integer_Type, Fractional_Type>`` (``src/mat/graph.hpp:33-67``)."""
 
@@ -107,16 +144,14 @@ class Graph:
 
     def load(self, filepath, nrows, ncols, directed=True, transpose=False, self_loops=True, acyclic=False,
              parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_):
-        """Binary edge list (``load_binary``, ``src/mat/graph.hpp:172-191``); the reference sniffs the type with
-        file(1) and also accepts text, which is ingest outside the hot path."""
-        rec = 3 if self.weighted else 2
-        data = np.fromfile(filepath, dtype="<u4")
-        if data.size % rec:
-            raise capi.GraphTapError(capi.GT_ERR_INVALID, f"{filepath}: size is not a multiple of the {rec * 4}-byte record")
-        return self.load_triples(data.reshape(-1, rec), nrows, directed, transpose, self_loops, acyclic,
-                                 parallel_edges, tiling_type, compression_type)
+        """``Graph::load`` (``src/mat/graph.hpp:104-148``): sniffs the file type (the reference shells out to
+        file(1): "ASCII" -> text, "data" -> binary) and reads the whole edge list; every rank builds its own
+        tiles from it (gt_graph_build)."""
+        triples = read_edge_list(filepath, self.weighted)
+        return self.load_triples(triples, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling_type, compression_type)
 
     load_binary = load
+    load_text = load
 
     def load_triples(self, triples: np.ndarray, nvertices, directed=True, transpose=False, self_loops=True, acyclic=False,
                      parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_):

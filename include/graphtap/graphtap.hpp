@@ -93,18 +93,16 @@ class Graph {
     gt_graph* handle = nullptr;
     static constexpr bool weighted = !std::is_same<Weight, Empty>::value;     // -DHAS_WEIGHT switches wp (src/apps/deg.h:13-17)
 
+    // Graph::load (src/mat/graph.hpp:104-148): the reference sniffs the type with file(1) ("ASCII" -> text, "data" -> binary)
     void load(std::string filepath, Integer_Type nrows, Integer_Type, bool directed = true, bool transpose = false, bool self_loops = true,
               bool acyclic = false, bool parallel_edges = true, Tiling_type tiling = _2DT_, Compression_type compression = _CSC_) {
         double t1 = Env::clock();
-        load_binary(filepath, nrows, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
+        if (looks_like_text(filepath)) load_text(filepath, nrows, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
+        else load_binary(filepath, nrows, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
         Env::print_time("Ingress", Env::clock() - t1);
     }
     void load_binary(std::string filepath, Integer_Type nrows, Integer_Type, bool directed, bool transpose, bool self_loops, bool acyclic,
                      bool parallel_edges, Tiling_type tiling, Compression_type compression) {
-        if (tiling != _2DT_ || (compression != _TCSC_ && compression != _TCSC_CF_)) {
-            fprintf(stderr, "graphtap_b200: only _2DT_ tiling with _TCSC_/_TCSC_CF_ compression runs on the device\n");
-            Env::exit(1);
-        }
         std::ifstream fin(filepath.c_str(), std::ios_base::binary);
         if (!fin.is_open()) { fprintf(stderr, "Unable to open input file\n"); Env::exit(1); }
         fin.seekg(0, std::ios_base::end);
@@ -112,11 +110,51 @@ class Graph {
         std::vector<uint32_t> triples(bytes / 4);
         fin.seekg(0, std::ios_base::beg);
         fin.read((char*) triples.data(), (std::streamsize) (bytes / rec * rec));
-        gt_graph_flags fl = {directed, transpose, self_loops, acyclic, parallel_edges};
-        if (gt_graph_build(Env::ctx, triples.data(), bytes / rec, weighted, 0, nrows, &fl, compression == _TCSC_ ? GT_TCSC : GT_TCSC_CF, &handle))
-            Env::fail("gt_graph_build");
-        if (Env::is_master) printf("\n%s: Read %lu edges\n", filepath.c_str(), (unsigned long) (bytes / rec));
+        build(filepath, triples, bytes / rec, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
     }
+    // text edge lists (src/mat/graph.hpp:194-304): '#'/'%' header lines, then "row col[ weight]" per line
+    void load_text(std::string filepath, Integer_Type nrows, Integer_Type, bool directed, bool transpose, bool self_loops, bool acyclic,
+                   bool parallel_edges, Tiling_type tiling, Compression_type compression) {
+        std::ifstream fin(filepath.c_str());
+        if (!fin.is_open()) { fprintf(stderr, "Unable to open input file\n"); Env::exit(1); }
+        std::vector<uint32_t> triples;
+        std::string line;
+        bool started = false;
+        const long want = weighted ? 3 : 2;
+        while (std::getline(fin, line)) {
+            if (!started) { if (line.empty() || line[0] == '#' || line[0] == '%') continue; started = true; }
+            if (line.empty()) break;
+            if (std::count(line.cbegin(), line.cend(), ' ') + 1 != want) { fprintf(stderr, "read() failure \"%s\"\n", line.c_str()); Env::exit(1); }
+            char* end = nullptr;
+            const char* p = line.c_str();
+            for (long f = 0; f < want; f++) { triples.push_back((uint32_t) std::strtoul(p, &end, 10)); p = end; }
+        }
+        build(filepath, triples, triples.size() / want, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
+    }
+  private:
+    static bool looks_like_text(const std::string& path) {
+        std::ifstream f(path.c_str(), std::ios_base::binary);
+        char buf[4096];
+        f.read(buf, sizeof(buf));
+        const std::streamsize n = f.gcount();
+        for (std::streamsize i = 0; i < n; i++) {
+            const unsigned char c = (unsigned char) buf[i];
+            if (!(c == '\n' || c == '\r' || c == '\t' || (c >= 32 && c < 127))) return false;
+        }
+        return n > 0;
+    }
+    void build(const std::string& filepath, std::vector<uint32_t>& triples, uint64_t n, Integer_Type nrows, bool directed, bool transpose,
+               bool self_loops, bool acyclic, bool parallel_edges, Tiling_type tiling, Compression_type compression) {
+        if (tiling != _2DT_ || (compression != _TCSC_ && compression != _TCSC_CF_)) {
+            fprintf(stderr, "graphtap_b200: only _2DT_ tiling with _TCSC_/_TCSC_CF_ compression runs on the device\n");
+            Env::exit(1);
+        }
+        gt_graph_flags fl = {directed, transpose, self_loops, acyclic, parallel_edges};
+        if (gt_graph_build(Env::ctx, triples.data(), n, weighted, 0, nrows, &fl, compression == _TCSC_ ? GT_TCSC : GT_TCSC_CF, &handle))
+            Env::fail("gt_graph_build");
+        if (Env::is_master) printf("\n%s: Read %lu edges\n", filepath.c_str(), (unsigned long) n);
+    }
+  public:
     void free() { if (handle) { gt_graph_free(handle); handle = nullptr; } }
 };
 

@@ -49,3 +49,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "gt_oracle" not in txt and "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_edge_list_readers(tmp_path):
+    """Host-side ingest of the reference's two file formats (src/mat/graph.hpp:194-372): binary records and
+    text with '#'/'%' headers; both must give the same records."""
+    import numpy as np
+    from graphtap_b200.engine import read_edge_list
+    rng = np.random.default_rng(3)
+    tri = rng.integers(0, 1000, size=(200, 3), dtype=np.uint32)
+    tri[:, 2] = tri[:, 2] % 128 + 1
+    for weighted in (False, True):
+        t = tri if weighted else tri[:, :2].copy()
+        b = tmp_path / f"g{int(weighted)}.bin"
+        t.tofile(b)
+        txt = tmp_path / f"g{int(weighted)}.txt"
+        with open(txt, "w") as f:
+            f.write("# comment\n% another\n\n")
+            for r in t:
+                f.write(" ".join(str(int(x)) for x in r) + "\n")
+            f.write("\n9 9 9\n")                     # after the first empty line: ignored, as in the reference
+        assert (read_edge_list(str(b), weighted) == t).all()
+        assert (read_edge_list(str(txt), weighted) == t).all()
+    bad = tmp_path / "bad.txt"
+    bad.write_text("1 2 3 4\n")
+    with pytest.raises(capi.GraphTapError):
+        read_edge_list(str(bad), False)
