@@ -135,6 +135,7 @@ def run_ours(args):
     import numpy as np
     from graphtap_b200 import capi, engine as E
 
+    E.Env.quiet = True                     # stdout carries exactly one JSON line
     E.Env.init()
     rank, nranks = E.Env.rank, E.Env.nranks
     dist = E.Env._dist

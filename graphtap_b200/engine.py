@@ -44,6 +44,7 @@ class Env:
     is_master = True
     ctx = None
     _dist = None
+    quiet = False          # True: no "Execute time" / checksum lines on stdout (bench.py prints exactly one JSON line)
 
     @classmethod
     def init(cls, device: int | None = None, use_torch_distributed: bool | None = None) -> None:
@@ -91,7 +92,7 @@ class Env:
 
     @classmethod
     def print_time(cls, preamble: str, seconds: float) -> None:
-        if cls.is_master:
+        if cls.is_master and not cls.quiet:
             print(f"{preamble} time: {seconds:f} seconds")
 
 
