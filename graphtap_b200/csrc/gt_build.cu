@@ -247,6 +247,12 @@ __global__ void k_tile_JA(const uint64_t* keys, uint64_t n, uint64_t tile_prefix
     }
 }
 
+__global__ void k_max_col_entries(const uint32_t* __restrict__ JA, uint32_t ncols, unsigned int* __restrict__ out) {
+    unsigned int m = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) m = max(m, JA[j + 1] - JA[j]);
+    if (m) atomicMax(out, m);
+}
+
 // chunk_col[k] = column that holds edge k*GT_PUSH_CHUNK (last column with JA[c] <= e)
 __global__ void k_chunk_cols(const uint32_t* JA, uint32_t ncols, uint64_t nnz, uint32_t nchunks, uint32_t* chunk_col) {
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k <= nchunks; k += gridDim.x * blockDim.x) {
@@ -534,6 +540,23 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     }
     GT_CUDA(cudaGetLastError());
     GT_CUDA(cudaStreamSynchronize(st));
+    {   // longest column per tile + scratch of the heavy-column path of the frontier SpMSpV
+        uint32_t maxcols = 1;
+        for (const SegMaps& c : g->cols) maxcols = std::max(maxcols, c.nnz);
+        g->heavy_list.alloc(maxcols);
+        g->heavy_count.alloc(1);
+        DevBuf<unsigned int> d_m; d_m.alloc(ntiles);
+        GT_CUDA(cudaMemsetAsync(d_m.p, 0, (size_t) ntiles * 4, st));
+        for (int k = 0; k < ntiles; k++) {
+            const Tile& T = g->tiles[k];
+            const uint32_t nc = g->cols[T.col_slot].nnz;
+            if (T.nnz && nc) { k_max_col_entries<<<grid_for(nc, 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, nc, d_m.p + k); ctx->kernel_launches++; }
+        }
+        std::vector<unsigned int> h_m(ntiles, 0);
+        GT_CUDA(cudaMemcpyAsync(h_m.data(), d_m.p, (size_t) ntiles * 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < ntiles; k++) g->tiles[k].max_col_entries = h_m[k];
+    }
 
     // nnz over all ranks
     g->nnz_global = g->nnz_local;

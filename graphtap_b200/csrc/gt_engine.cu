@@ -287,7 +287,16 @@ static void launch_spmspv(gt_ctx* ctx, const gt_graph* g, const Tile& T, int sem
     const uint32_t* IA = g->IA_pool.p + T.offset;
     const uint32_t* A = g->weighted ? g->A_pool.p + T.offset : nullptr;
     const int grid = grid_for((uint64_t) k * 32, 256, ctx->sm_count, 8);
-#define GT_SP(S, W) k_spmspv_push<S, W><<<grid, 256, 0, st>>>(T.JA.p, IA, A, xi, (const Semiring<S>::T*) xv, k, (Semiring<S>::T*) y, t)
+    // heavy-column path only where a column of this tile can exceed the threshold (one extra launch otherwise)
+    const bool heavy = T.max_col_entries > kHeavyColumn;
+    uint32_t* hl = heavy ? g->heavy_list.p : nullptr;
+    unsigned int* hc = heavy ? g->heavy_count.p : nullptr;
+    if (heavy) GT_CUDA(cudaMemsetAsync(hc, 0, sizeof(unsigned int), st));
+    const int hgrid = ctx->sm_count * 4;
+#define GT_SP(S, W) do { \
+        k_spmspv_push<S, W><<<grid, 256, 0, st>>>(T.JA.p, IA, A, xi, (const Semiring<S>::T*) xv, k, (Semiring<S>::T*) y, t, hl, hc); \
+        if (heavy) { k_spmspv_heavy<S, W><<<hgrid, 256, 0, st>>>(T.JA.p, IA, A, xi, (const Semiring<S>::T*) xv, (Semiring<S>::T*) y, t, hl, hc); ctx->kernel_launches++; } \
+    } while (0)
     if (semiring == GT_PLUS_TIMES_F64) { if (A) GT_SP(GT_PLUS_TIMES_F64, true); else GT_SP(GT_PLUS_TIMES_F64, false); }
     else if (semiring == GT_MIN_PLUS_U32) { GT_REQUIRE(A, "min-plus needs a weighted graph"); GT_SP(GT_MIN_PLUS_U32, true); }
     else { if (A) GT_SP(GT_MIN_SELECT_U32, true); else GT_SP(GT_MIN_SELECT_U32, false); }

@@ -31,6 +31,7 @@ struct Tile {
     uint64_t offset = 0;           // into IA_pool / A_pool, multiple of 4 entries (128-bit loads)
     DevBuf<uint32_t> JA;           // [cols[col_slot].nnz + 1]
     DevBuf<uint32_t> chunk_col;    // first column of every GT_PUSH_CHUNK-edge chunk (+ sentinel)
+    uint32_t max_col_entries = 0;  // longest column of the tile (decides whether the heavy-column path can trigger)
 };
 
 struct PullLayout;
@@ -49,6 +50,8 @@ struct gt_graph {
     std::vector<gt::SegMaps> rows, cols;     // by local slot
     std::vector<gt::Tile> tiles;             // local_tiles_row_order
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
+    gt::DevBuf<uint32_t> heavy_list;         // frontier SpMSpV scratch: positions of heavy columns in the frontier + a counter
+    gt::DevBuf<unsigned int> heavy_count;
     std::vector<gt::HotOrder> hot;           // one per distinct local segment
     std::vector<int> hot_of_row_slot, hot_of_col_slot;
     gt::PullLayout* pull = nullptr;          // derived layout of the plus-times SpMV, built on first use (gt_pull.cu)

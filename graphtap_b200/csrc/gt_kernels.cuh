@@ -179,13 +179,18 @@ k_spmv_pull(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, co
 }
 
 // ---- frontier SpMSpV: only the k active columns ---------------------------------------------------------
-// One warp per frontier column (RMAT hubs are split across the warp's lanes; columns of a frontier are
-// independent, so the grid is as wide as the frontier).
+// Body: one warp per frontier column, lanes stride the column's entries (columns of a frontier are independent,
+// so the grid is as wide as the frontier).  RMAT hubs: a column with more than kHeavyColumn entries is not walked
+// by its warp but appended to a short list, and a second launch gives every listed column a whole CTA (block
+// path for heavy columns), so one 10^5-entry hub cannot serialise an iteration behind a single warp.
+constexpr uint32_t kHeavyColumn = 16384;
+
 template <int S, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 k_spmspv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
               const uint32_t* __restrict__ xi, const typename Semiring<S>::T* __restrict__ xv, uint32_t k,
-              typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t) {
+              typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t,
+              uint32_t* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count) {
     typedef Semiring<S> SR;
     typedef typename SR::T T;
     const int lane = threadIdx.x & 31;
@@ -194,7 +199,33 @@ k_spmspv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, 
         const uint32_t j = xi[f];
         const T v = xv[f];
         const uint32_t b = JA[j], e = JA[j + 1];
+        if (heavy_list && e - b > kHeavyColumn) {
+            if (lane == 0) heavy_list[atomicAdd(heavy_count, 1u)] = f;
+            continue;
+        }
         for (uint32_t i = b + lane; i < e; i += 32) {
+            const uint32_t r = IA[i];
+            SR::reduce(y + r, WEIGHTED ? SR::mul(v, A[i]) : v);
+            if (t) t[r] = 1;
+        }
+    }
+}
+
+template <int S, bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+k_spmspv_heavy(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
+               const uint32_t* __restrict__ xi, const typename Semiring<S>::T* __restrict__ xv,
+               typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t,
+               const uint32_t* __restrict__ heavy_list, const unsigned int* __restrict__ heavy_count) {
+    typedef Semiring<S> SR;
+    typedef typename SR::T T;
+    const unsigned int n = *heavy_count;
+    for (unsigned int h = blockIdx.x; h < n; h += gridDim.x) {          // one CTA per heavy column
+        const uint32_t f = heavy_list[h];
+        const uint32_t j = xi[f];
+        const T v = xv[f];
+        const uint32_t b = JA[j], e = JA[j + 1];
+        for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
             const uint32_t r = IA[i];
             SR::reduce(y + r, WEIGHTED ? SR::mul(v, A[i]) : v);
             if (t) t[r] = 1;

@@ -232,6 +232,10 @@ def test_edge_cases():
         "duplicates": (np.array([[1, 2], [2, 1], [1, 2], [1, 2], [5, 6], [0, 7]], dtype="<u4"), 8),
         "star_hub": (np.stack([np.zeros(5000, dtype="<u4"), np.arange(1, 5001, dtype="<u4")], axis=1), 5001),
         "chain": (np.stack([np.arange(0, 300, dtype="<u4"), np.arange(1, 301, dtype="<u4")], axis=1), 301),
+        # a frontier column longer than kHeavyColumn (16384): the CTA-per-column heavy path of the SpMSpV
+        "big_hub": (np.concatenate([np.stack([np.zeros(40000, dtype="<u4"), np.arange(1, 40001, dtype="<u4")], axis=1),
+                                    np.stack([np.arange(1, 40000, dtype="<u4"), np.arange(2, 40001, dtype="<u4")], axis=1)[::7],
+                                    np.array([[40001, 0]], dtype="<u4")]), 40002),
         "max_vertex_id": (np.array([[0, 1023], [1023, 0], [1023, 1023]], dtype="<u4"), 1023),
     }
     for name, (tri, n) in cases.items():
