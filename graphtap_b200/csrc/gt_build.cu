@@ -541,9 +541,9 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     GT_CUDA(cudaGetLastError());
     GT_CUDA(cudaStreamSynchronize(st));
     {   // longest column per tile + scratch of the heavy-column path of the frontier SpMSpV
-        uint32_t maxcols = 1;
-        for (const SegMaps& c : g->cols) maxcols = std::max(maxcols, c.nnz);
-        g->heavy_list.alloc(maxcols);
+        uint64_t maxnnz = 0;                      // every listed chunk holds > kHeavyChunk/2 entries of its tile
+        for (const Tile& T : g->tiles) maxnnz = std::max(maxnnz, T.nnz);
+        g->heavy_list.alloc(maxnnz / 4096 + 64);
         g->heavy_count.alloc(1);
         DevBuf<unsigned int> d_m; d_m.alloc(ntiles);
         GT_CUDA(cudaMemsetAsync(d_m.p, 0, (size_t) ntiles * 4, st));

@@ -85,25 +85,34 @@ __global__ void k_messenger_u32(VState V, int app, uint32_t vid0, const uint32_t
         x[j] = m;
     }
 }
-// frontier list of one x segment: xi = compressed ids with x != INF, xv = their values (:744-748);
-// order inside the list is irrelevant to a min reduction
-__global__ void __launch_bounds__(256) k_frontier(const uint32_t* __restrict__ x, uint32_t nc, uint32_t* __restrict__ xi, uint32_t* __restrict__ xv,
-                                                   unsigned int* __restrict__ count) {
-    const uint32_t n_round = (nc + 31) / 32 * 32;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += gridDim.x * blockDim.x) {
-        const uint32_t v = j < nc ? x[j] : GT_INF_U32;
-        const bool act = v != GT_INF_U32;
-        const unsigned ballot = __ballot_sync(0xffffffffu, act);
-        if (!ballot) continue;
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(count, (unsigned) __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (act) {
-            const unsigned pos = base + __popc(ballot & ((1u << lane) - 1));
-            xi[pos] = j;
-            xv[pos] = v;
+// frontier list of one x segment: xi = compressed ids with x != INF, xv = their values (:744-748); order inside
+// the list is irrelevant to a min reduction.  One atomic per CTA per 4096 elements (block scan of the per-thread
+// counts), not per warp: with millions of active columns per-warp atomics on one counter cost 0.3 ms a pass.
+__global__ void __launch_bounds__(1024) k_frontier(const uint32_t* __restrict__ x, uint32_t nc, uint32_t* __restrict__ xi, uint32_t* __restrict__ xv,
+                                                    unsigned int* __restrict__ count) {
+    typedef cub::BlockScan<unsigned, 1024> BS;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ unsigned base_s;
+    const uint32_t per_iter = 1024 * 4;
+    for (uint32_t start = blockIdx.x * per_iter; start < nc; start += gridDim.x * per_iter) {
+        const uint32_t j0 = start + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = (j0 + u < nc) ? x[j0 + u] : GT_INF_U32;
+        unsigned mine = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) mine += v[u] != GT_INF_U32;
+        unsigned off, total;
+        BS(tmp).ExclusiveSum(mine, off, total);
+        if (threadIdx.x == 0 && total) base_s = atomicAdd(count, total);
+        __syncthreads();
+        if (total) {
+            unsigned pos = base_s + off;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (v[u] != GT_INF_U32) { xi[pos] = j0 + u; xv[pos] = v[u]; pos++; }
         }
+        __syncthreads();
     }
 }
 
@@ -289,7 +298,7 @@ static void launch_spmspv(gt_ctx* ctx, const gt_graph* g, const Tile& T, int sem
     const int grid = grid_for((uint64_t) k * 32, 256, ctx->sm_count, 8);
     // heavy-column path only where a column of this tile can exceed the threshold (one extra launch otherwise)
     const bool heavy = T.max_col_entries > kHeavyColumn;
-    uint32_t* hl = heavy ? g->heavy_list.p : nullptr;
+    uint2* hl = heavy ? g->heavy_list.p : nullptr;
     unsigned int* hc = heavy ? g->heavy_count.p : nullptr;
     if (heavy) GT_CUDA(cudaMemsetAsync(hc, 0, sizeof(unsigned int), st));
     const int hgrid = ctx->sm_count * 4;
@@ -569,7 +578,7 @@ static void scatter_gather(gt_program* P) {
         for (size_t k = 0; k < P->X.size(); k++) {
             const SegMaps& s = (*P->pcol)[k];
             if (!s.nnz) continue;
-            k_frontier<<<grid_for(s.nnz, 256, ctx->sm_count), 256, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->XI[k].p, P->XV[k].p, P->d_counts.p + k);
+            k_frontier<<<grid_for((s.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->XI[k].p, P->XV[k].p, P->d_counts.p + k);
             ctx->kernel_launches++;
         }
         GT_CUDA(cudaMemcpyAsync(P->h_counts, P->d_counts.p, P->X.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));

@@ -50,7 +50,7 @@ struct gt_graph {
     std::vector<gt::SegMaps> rows, cols;     // by local slot
     std::vector<gt::Tile> tiles;             // local_tiles_row_order
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
-    gt::DevBuf<uint32_t> heavy_list;         // frontier SpMSpV scratch: positions of heavy columns in the frontier + a counter
+    gt::DevBuf<uint2> heavy_list;            // frontier SpMSpV scratch: (frontier position, chunk) of heavy columns + a counter
     gt::DevBuf<unsigned int> heavy_count;
     std::vector<gt::HotOrder> hot;           // one per distinct local segment
     std::vector<int> hot_of_row_slot, hot_of_col_slot;

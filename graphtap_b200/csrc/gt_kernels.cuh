@@ -181,16 +181,18 @@ k_spmv_pull(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, co
 // ---- frontier SpMSpV: only the k active columns ---------------------------------------------------------
 // Body: one warp per frontier column, lanes stride the column's entries (columns of a frontier are independent,
 // so the grid is as wide as the frontier).  RMAT hubs: a column with more than kHeavyColumn entries is not walked
-// by its warp but appended to a short list, and a second launch gives every listed column a whole CTA (block
-// path for heavy columns), so one 10^5-entry hub cannot serialise an iteration behind a single warp.
+// by its warp; the warp appends one (frontier position, chunk) pair per kHeavyChunk entries to a list, and a second
+// launch gives every pair a CTA (block path for heavy columns), so a 10^5..10^6-entry hub is spread over the whole
+// grid instead of serialising an iteration behind a single warp.
 constexpr uint32_t kHeavyColumn = 16384;
+constexpr uint32_t kHeavyChunk = 8192;
 
 template <int S, bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 k_spmspv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
               const uint32_t* __restrict__ xi, const typename Semiring<S>::T* __restrict__ xv, uint32_t k,
               typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t,
-              uint32_t* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count) {
+              uint2* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count) {
     typedef Semiring<S> SR;
     typedef typename SR::T T;
     const int lane = threadIdx.x & 31;
@@ -200,7 +202,11 @@ k_spmspv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, 
         const T v = xv[f];
         const uint32_t b = JA[j], e = JA[j + 1];
         if (heavy_list && e - b > kHeavyColumn) {
-            if (lane == 0) heavy_list[atomicAdd(heavy_count, 1u)] = f;
+            const uint32_t nchunks = (e - b + kHeavyChunk - 1) / kHeavyChunk;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(heavy_count, nchunks);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t c = lane; c < nchunks; c += 32) heavy_list[base + c] = make_uint2(f, c);
             continue;
         }
         for (uint32_t i = b + lane; i < e; i += 32) {
@@ -216,15 +222,15 @@ __global__ void __launch_bounds__(256)
 k_spmspv_heavy(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
                const uint32_t* __restrict__ xi, const typename Semiring<S>::T* __restrict__ xv,
                typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t,
-               const uint32_t* __restrict__ heavy_list, const unsigned int* __restrict__ heavy_count) {
+               const uint2* __restrict__ heavy_list, const unsigned int* __restrict__ heavy_count) {
     typedef Semiring<S> SR;
     typedef typename SR::T T;
     const unsigned int n = *heavy_count;
-    for (unsigned int h = blockIdx.x; h < n; h += gridDim.x) {          // one CTA per heavy column
-        const uint32_t f = heavy_list[h];
-        const uint32_t j = xi[f];
-        const T v = xv[f];
-        const uint32_t b = JA[j], e = JA[j + 1];
+    for (unsigned int h = blockIdx.x; h < n; h += gridDim.x) {          // one CTA per (heavy column, chunk)
+        const uint2 fc = heavy_list[h];
+        const uint32_t j = xi[fc.x];
+        const T v = xv[fc.x];
+        const uint32_t b = JA[j] + fc.y * kHeavyChunk, e = min(JA[j + 1], b + kHeavyChunk);
         for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
             const uint32_t r = IA[i];
             SR::reduce(y + r, WEIGHTED ? SR::mul(v, A[i]) : v);
