@@ -5,8 +5,9 @@
 // issues, per iteration: Ibcast of every x segment along the column group
 // (src/vp/vertex_program.hpp:843-862,970-1013), a follower->leader send of every partial y along the
 // row group with the reduction done by the leader (:1083-1108,1522-1573), and a world Allreduce for
-// convergence (:1918).  Here those are ncclBroadcast / ncclReduce / ncclAllReduce on communicators
-// split with the same rank lists.
+// convergence (:1918).  Here those are ONE in-place ncclAllGather (x, column group), ONE in-place
+// ncclReduceScatter (y, row group) and an ncclAllReduce per iteration, on communicators split with the
+// same rank lists (every member of a group leads exactly one of the group's segments).
 //
 // NCCL is bound with dlopen("libnccl.so.2") so that (a) inside a Python process the copy torch already
 // loaded is reused (one NCCL per process), (b) a single-GPU run needs no NCCL at all, and (c) the

@@ -3,13 +3,15 @@
 // The reference loop (src/vp/vertex_program.hpp:407-441):
 //     while (true) { scatter_gather(); combine(); apply(); iteration++; converged? }
 // and what each phase becomes here:
-//   scatter_gather   messenger kernel over the owned column segment's non-empty columns (:687-758),
-//                    then ncclBroadcast of every local x segment along the column group (:843-862,970-1013)
+//   scatter_gather   messenger kernel over the owned column segment's non-empty columns (:687-758), then ONE in-place
+//                    ncclAllGather along the column group: x is laid out as one chunk per group member, chunk q =
+//                    the segment led by group rank q (the reference: one Ibcast per segment, :843-862,970-1013)
 //   combine          per local tile, in local_tiles_row_order: push SpMV / frontier SpMSpV (:1057-1113,
-//                    :1330-1434), then ncclReduce of every local y segment to its leader along the row group
-//                    (the follower->leader Isend + leader-side combine of :1083-1108,1522-1573)
+//                    :1330-1434) — PageRank: the pull SpMV of gt_pull.cu — then ONE in-place ncclReduceScatter
+//                    along the row group (the follower->leader Isend + leader-side combine of :1083-1108,1522-1573)
 //   apply            applicator kernel on the owned segment (:1640-1802), activity flags C
-//   has_converged    device count of C, ncclAllReduce over the world, one 8-byte D2H (:1884-1923)
+//   has_converged    device count of C, ncclAllReduce over the world, one 8-byte D2H (:1884-1923); for the
+//                    non-stationary programs it shares one stream synchronisation with the frontier sizes
 // The five shipped programs are recognised by enum; their messenger/combiner/applicator bodies
 // (src/apps/{deg,pr,bfs,cc,sssp}.h) are the __device__ functions below.  With GT_COL every row/column
 // notion swaps, including the two communicators (:279-325).

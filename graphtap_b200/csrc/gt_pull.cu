@@ -18,10 +18,14 @@
 //     index loads and neighbouring lanes have (nearly) equal trip counts.  Rows longer than `vrow`
 //     entries are cut into virtual rows whose partial sums meet in y through one RED.ADD each
 //     (<= degree/vrow per row), which bounds the skew a warp can see.
-//   * No shared-memory staging of x by default: a large carve-out shrinks L1, and L1's capacity bounds
-//     the number of gather misses in flight (ncu: MIO throttle 100 %, L1TEX 23 % with a 200 KB cache vs
-//     84 % without; profiles/r01_ncu_pull_s26_hot*.txt).  The kernel is bound by L1TEX sector throughput
-//     (one 32-byte sector per edge per clock per SM), which is the structural limit of a gather design.
+//   * No shared-memory staging of x: a large carve-out shrinks L1, and L1's capacity bounds the number of
+//     gather misses in flight (ncu: MIO throttle 100 %, L1TEX 23 % with a 200 KB cache vs 84 % without;
+//     profiles/r01_ncu_pull_s26_hot*.txt).  The kernel is bound by the L1-miss -> L2 gather path: one 32-byte
+//     sector per edge, ~280 G gathers/s per GPU (~12.9 TB/s of L2 sector traffic), the structural limit of a
+//     gather design.  L2 eviction hints (index stream evict-first, x evict-last) are worth 8 %.
+//   * Multi-GPU: x is one equal-sized chunk per member of the column group, so the exchange is a single in-place
+//     all-gather; entries whose column lies in this rank's own chunk form a separate SELL array that runs while
+//     the all-gather of the other chunks is in flight.
 //
 // Results: each row's sum is formed in a fixed order by one lane (split rows excepted), so it differs from
 // the reference's column-order sum only by f64 rounding, ~1e-16 relative — inside the 1e-6 contract.
