@@ -376,3 +376,18 @@ def test_sparse_and_dense_paths_agree():
             assert res[ratio][0] == res[0.0][0]
             for f in res[ratio][1].dtype.names:
                 assert (res[ratio][1][f] == res[0.0][1][f]).all()
+
+
+def test_degree_program_standalone(fixture_unweighted, golden_fixture):
+    """src/apps/deg.cpp: Deg with _ROW_ ordering on the untransposed matrix = out-degree including duplicates and
+    self loops; checksum 16384 / reachable 571, maximum 1983 at vertex 613."""
+    E = _E()
+    G = E.Graph(weighted=False)
+    G.load_triples(fixture_unweighted, 1024, directed=True, transpose=False, self_loops=True, parallel_edges=True, compression_type=E._TCSC_)
+    V = E.Deg_Program(G, True, False, False, E._ROW_)
+    assert V.execute(1) == 1
+    d = V.V["degree"]
+    assert (d[:1025] == golden_fixture["deg_np1_V"]).all()
+    assert V.checksum(quiet=True) == (16384, 571)
+    assert int(d.max()) == 1983 and int(d.argmax()) == 613
+    V.free(); G.free()
