@@ -90,6 +90,7 @@ PROTOTYPES = {
     "gt_graph_tile_view": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TileView)]),
     "gt_graph_rowgrp_maps": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "gt_graph_colgrp_maps": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    "gt_graph_classify": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "gt_tile_spmv": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gt_tile_spmspv": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gt_program_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),

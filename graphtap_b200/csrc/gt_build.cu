@@ -645,6 +645,38 @@ extern "C" int gt_graph_tile_view(gt_graph* g, uint32_t local_tile, gt_tile_view
     });
 }
 
+namespace gt {
+__global__ void k_classify(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, uint32_t th, unsigned int* __restrict__ out) {
+    unsigned int reg = 0, src = 0, snk = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        const bool r = I[i], c = J[i];
+        reg += r && c; src += r && !c; snk += !r && c;
+    }
+    if (reg) atomicAdd(out, reg);
+    if (src) atomicAdd(out + 1, src);
+    if (snk) atomicAdd(out + 2, snk);
+}
+}  // namespace gt
+
+extern "C" int gt_graph_classify(gt_graph* g, uint32_t* regular, uint32_t* source_rows, uint32_t* sink_columns) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g, "gt_graph_classify: NULL graph");
+        GT_CUDA(cudaSetDevice(g->ctx->device));
+        const uint32_t th = g->lay.info.tile_height;
+        gt::DevBuf<unsigned int> d; d.alloc(3);
+        GT_CUDA(cudaMemsetAsync(d.p, 0, 12, g->ctx->stream));
+        gt::k_classify<<<gt::grid_for(th, 256, g->ctx->sm_count), 256, 0, g->ctx->stream>>>(
+            g->rows[g->lay.info.accu_segment_row].bits.p, g->cols[g->lay.info.accu_segment_col].bits.p, th, d.p);
+        g->ctx->kernel_launches++;
+        unsigned int h[3];
+        GT_CUDA(cudaMemcpyAsync(h, d.p, 12, cudaMemcpyDeviceToHost, g->ctx->stream));
+        GT_CUDA(cudaStreamSynchronize(g->ctx->stream));
+        if (regular) *regular = h[0];
+        if (source_rows) *source_rows = h[1];
+        if (sink_columns) *sink_columns = h[2];
+    });
+}
+
 extern "C" int gt_graph_rowgrp_maps(gt_graph* g, uint32_t row_slot, const uint8_t** I, const uint32_t** IV, uint32_t* nnzrows) {
     return gt::guarded([&] {
         GT_REQUIRE(g && row_slot < g->rows.size(), "gt_graph_rowgrp_maps: slot out of range");

@@ -169,6 +169,12 @@ GT_API int gt_graph_tile_view(gt_graph* g, uint32_t local_tile, gt_tile_view* ou
 GT_API int gt_graph_rowgrp_maps(gt_graph* g, uint32_t row_slot, const uint8_t** I, const uint32_t** IV, uint32_t* nnzrows);
 GT_API int gt_graph_colgrp_maps(gt_graph* g, uint32_t col_slot, const uint8_t** J, const uint32_t** JV, uint32_t* nnzcols);
 
+/* classify_vertices on the owned segment (src/mat/matrix.hpp:1124-1144): regular = row and column non-empty, source
+ * rows = row non-empty / column empty, sink columns = row empty / column non-empty.  These are the sets the
+ * reference's _TCSC_CF_ "computation filtering" schedules by (src/vp/vertex_program.hpp:1218-1325); on the device
+ * _TCSC_CF_ graphs run the _TCSC_ schedule, which gives bit-identical results in fixed-iteration mode. */
+GT_API int gt_graph_classify(gt_graph* g, uint32_t* regular, uint32_t* source_rows, uint32_t* sink_columns);
+
 /* ---- kernel level: replaces Vertex_Program::spmv_stationary / spmv_nonstationary -----------------
  * (src/vp/vertex_program.hpp:96-105,1115-1327,1437-1506).  x and y are device vectors in the tile's
  * compressed spaces (|x| = nnzcols, |y| = nnzrows; with GT_COL the roles swap, :1175-1183).

@@ -391,3 +391,18 @@ def test_degree_program_standalone(fixture_unweighted, golden_fixture):
     assert V.checksum(quiet=True) == (16384, 571)
     assert int(d.max()) == 1983 and int(d.argmax()) == 613
     V.free(); G.free()
+
+
+def test_vertex_classification_matches_reference(fixture_unweighted):
+    """classify_vertices (src/mat/matrix.hpp:1124-1144) on the fixture with PageRank's flags: the reference's own
+    filter statistics are 866 non-empty rows = 550 regular + 316 source, 571 non-empty columns = 550 regular + 21 sink
+    (singlenode TCSC stats)."""
+    from graphtap_b200 import capi
+    E = _E()
+    G = E.Graph(weighted=False)
+    G.load_triples(fixture_unweighted, 1024, directed=True, transpose=True, self_loops=True, parallel_edges=True, compression_type=E._TCSC_CF_)
+    reg, src, snk = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    capi.check(capi.lib().gt_graph_classify(G.handle, C.byref(reg), C.byref(src), C.byref(snk)))
+    assert (reg.value, src.value, snk.value) == (550, 316, 21)
+    assert G.rowgrp_maps(0)[2] == 866 and G.colgrp_maps(0)[2] == 571
+    G.free()
