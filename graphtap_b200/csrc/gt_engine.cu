@@ -22,6 +22,7 @@
 // column segment (:1475), so `sparse_iterations` matches the reference's schedule.
 #include "gt_kernels.cuh"
 #include "gt_pull.h"
+#include "gt_peer.h"
 #include <cub/cub.cuh>
 #include <memory>
 #include <algorithm>
@@ -195,7 +196,10 @@ __global__ void k_pr_messenger_h(const double* __restrict__ rank_h, const uint32
         x[k] = d ? rank_h[k] / (double) d : 0.0;
     }
 }
-__global__ void __launch_bounds__(256) k_pr_apply_h(const double* __restrict__ y, double* __restrict__ rank_h, const uint32_t* __restrict__ deg_h,
+// partial y vectors of the owned row segment that the other members of the row group have put into this rank's
+// window (gt_peer.cu); the leader's combine (:1522-1541) is folded into the applicator's read
+struct YParts { const double* p[8]; int n; };
+__global__ void __launch_bounds__(256) k_pr_apply_h(const double* __restrict__ y, YParts yr, double* __restrict__ rank_h, const uint32_t* __restrict__ deg_h,
                                                      const uint8_t* __restrict__ flag_h, uint8_t* __restrict__ C_h, double* __restrict__ x, uint32_t n,
                                                      double alpha, double tol, unsigned long long* __restrict__ active) {
     unsigned local = 0;
@@ -203,7 +207,9 @@ __global__ void __launch_bounds__(256) k_pr_apply_h(const double* __restrict__ y
         double r = rank_h[k];
         uint8_t c = 0;
         if (flag_h[k]) {                                   // row non-empty: applicator(state, y)
-            const double nw = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, y[k]));
+            double yk = y[k];
+            for (int j = 0; j < yr.n; j++) yk += yr.p[j][k];
+            const double nw = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, yk));
             c = fabs(nw - r) > tol;
             rank_h[k] = nw;
             r = nw;
@@ -347,6 +353,17 @@ struct gt_program {
     // pull mode: x / y in hot order, and the owned segment's state in hot order while execute() runs
     gt::DevBuf<double> Xh;                         // concatenated hot-ordered x of the local column segments (+ one 0.0)
     gt::DevBuf<double> Yh;                         // concatenated y chunks of the local row segments
+    // NVLink peer exchange (gt_peer.cu).  wx: the members of the column group put their x chunk into each other's
+    // window, two buffers alternating by epoch parity (a rank one iteration ahead writes x(k+1) while a slower one
+    // still reads x(k)).  wy: followers put the partial y of a row segment into its leader's window, one slot per
+    // sender, again two parities.  Without a window the same exchange is one ncclAllGather / ncclReduceScatter.
+    gt::PeerWindow* wx = nullptr;
+    gt::PeerWindow* wy = nullptr;
+    double* xbuf[2] = {nullptr, nullptr};          // the x buffer of each parity (both = Xh.p without wx)
+    size_t x_stride = 0;                           // doubles between the two x buffers inside wx
+    uint32_t x_epoch = 0, y_epoch = 0;             // puts issued so far (= the value the arrival counters must reach)
+    bool x_wait_pending = false, ypush_pending = false, pull_ready = false;
+    cudaEvent_t ev_b = nullptr, ev_ypush = nullptr;
     gt::DevBuf<double> rank_h;
     gt::DevBuf<uint32_t> deg_h;
     gt::DevBuf<uint8_t> flag_h, C_h;
@@ -425,9 +442,39 @@ static void prog_alloc(gt_program* P) {
     P->d_active.alloc(2);
     P->d_counts.alloc(std::max<size_t>(1, P->X.size()));
     GT_CUDA(cudaMallocHost((void**) &P->h_active, 2 * sizeof(unsigned long long)));
+    P->h_active[0] = P->h_active[1] = 0;
     GT_CUDA(cudaMallocHost((void**) &P->h_counts, std::max<size_t>(1, P->X.size()) * sizeof(unsigned int)));
     GT_CUDA(cudaEventCreate(&P->ev0));
     GT_CUDA(cudaEventCreate(&P->ev1));
+}
+
+// x / y of the pull path.  Multi-GPU: windows the other group members write into over NVLink (GT_PEER=0 or a failed
+// cudaIpc mapping -> plain buffers + NCCL collectives; every rank takes the same branch, peer_window_create agrees).
+static void pull_alloc(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->stream;
+    const PullLayout* L = P->pull;
+    const int S = ctx->comm ? comm_size_in(ctx->comm, P->bcast_group) : 1;
+    const int G = ctx->comm ? comm_size_in(ctx->comm, P->reduce_group) : 1;
+    const char* e = getenv("GT_PEER");
+    const bool want_peer = ctx->comm && !(e && atoi(e) == 0) && S <= 8 && G <= 8;
+    P->x_stride = ((size_t) L->xlen + 2) / 2 * 2;                 // x[xlen] is the permanent 0.0 the padding codes point at
+    if (want_peer && S > 1) P->wx = peer_window_create(ctx, P->bcast_group, 2 * P->x_stride * sizeof(double));
+    if (want_peer && G > 1) P->wy = peer_window_create(ctx, P->reduce_group, 2 * (size_t) G * L->ychunk * sizeof(double));
+    if (P->wx) {
+        P->xbuf[0] = (double*) P->wx->local;
+        P->xbuf[1] = P->xbuf[0] + P->x_stride;
+    } else {
+        P->Xh.alloc((size_t) L->xlen + 1);
+        GT_CUDA(cudaMemsetAsync(P->Xh.p, 0, P->Xh.bytes(), st));
+        P->xbuf[0] = P->xbuf[1] = P->Xh.p;
+    }
+    P->Yh.alloc(L->ylen);
+    P->own_hot = &P->g->hot[P->g->hot_of_row_slot[P->own_row_slot]];
+    P->rank_h.alloc(P->own_hot->n); P->deg_h.alloc(P->own_hot->n); P->flag_h.alloc(P->own_hot->n); P->C_h.alloc(P->own_hot->n);
+    GT_CUDA(cudaEventCreateWithFlags(&P->ev_b, cudaEventDisableTiming));
+    GT_CUDA(cudaEventCreateWithFlags(&P->ev_ypush, cudaEventDisableTiming));
+    P->pull_ready = true;
 }
 
 // init_stationary + init_nonstationary (:504-636)
@@ -447,13 +494,7 @@ static void prog_initialize(gt_program* P) {
     if (P->app == GT_APP_PR && P->ordering == GT_ROW && !P->g->weighted && P->pr_layout == 1) {
         if (!P->g->pull) P->g->pull = pull_build(P->g);
         P->pull = P->g->pull;
-        if (!P->Xh.p) {
-            P->Xh.alloc((size_t) P->pull->xlen + 1);
-            GT_CUDA(cudaMemsetAsync(P->Xh.p, 0, P->Xh.bytes(), st));
-            P->Yh.alloc(P->pull->ylen);
-            P->own_hot = &P->g->hot[P->g->hot_of_row_slot[P->own_row_slot]];
-            P->rank_h.alloc(P->own_hot->n); P->deg_h.alloc(P->own_hot->n); P->flag_h.alloc(P->own_hot->n); P->C_h.alloc(P->own_hot->n);
-        }
+        if (!P->pull_ready) pull_alloc(P);
     }
     P->hot_valid = false;
     P->x_ready = false;
@@ -512,19 +553,33 @@ static void pull_state_out(gt_program* P) {
     GT_CUDA(cudaGetLastError());
 }
 
+// x buffer the current iteration reads (parity of the last put) / the one the next messenger writes
+static inline double* pull_x_cur(gt_program* P) { return P->xbuf[P->wx ? (P->x_epoch & 1) : 0]; }
+static inline double* pull_x_next(gt_program* P) { return P->xbuf[P->wx ? ((P->x_epoch + 1) & 1) : 0]; }
+
 static void pull_scatter_gather(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     pull_state_in(P);
     const uint32_t n = P->own_hot->n;
-    double* xo = P->Xh.p + P->pull->xoff[P->own_col_slot];
+    double* xo = pull_x_next(P) + P->pull->xoff[P->own_col_slot];
     if (!P->x_ready && n) {                           // later iterations: x was written by the fused applicator
         k_pr_messenger_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->rank_h.p, P->deg_h.p, n, xo);
         ctx->kernel_launches++;
     }
     P->x_ready = true;
     P->ag_pending = false;
-    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
+    if (P->wx) {
+        // bcast_stationary (:843-862) as puts: the own chunk goes into every other member's window by copy engine,
+        // on the side stream, while this rank's SpMV over its own chunk is already running
+        P->x_epoch++;
+        GT_CUDA(cudaEventRecord(ctx->ev_x, st));
+        GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x, 0));
+        const size_t off = ((size_t) (P->x_epoch & 1) * P->x_stride + P->pull->xoff[P->own_col_slot]) * sizeof(double);
+        for (int j = 1; j < P->wx->size; j++)
+            peer_put(ctx, P->wx, (P->wx->me + j) % P->wx->size, off, xo, (size_t) n * sizeof(double), P->x_epoch, ctx->comm_stream);
+        P->x_wait_pending = true;
+    } else if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
         // the all-gather runs on its own stream; the SpMV over the own chunk does not wait for it
         GT_CUDA(cudaEventRecord(ctx->ev_x, st));
         GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x, 0));
@@ -535,27 +590,62 @@ static void pull_scatter_gather(gt_program* P) {
     GT_CUDA(cudaGetLastError());
 }
 
+// the other members' x chunks have landed (no-op when nothing is in flight)
+static void pull_x_arrived(gt_program* P) {
+    gt_ctx* ctx = P->ctx;
+    if (P->x_wait_pending) { peer_wait_all(ctx, P->wx, P->x_epoch, ctx->stream); P->x_wait_pending = false; }
+    if (P->ag_pending) { GT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ag, 0)); P->ag_pending = false; }
+}
+
 static void pull_combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
+    const PullLayout* L = P->pull;
+    const double* x = pull_x_cur(P);
+    const size_t R = L->rows.size();
+    const size_t own = (size_t) P->own_row_slot;
+    if (P->ypush_pending) { GT_CUDA(cudaStreamWaitEvent(st, P->ev_ypush, 0)); P->ypush_pending = false; }   // last put has read Yh
     if (P->Yh.n) GT_CUDA(cudaMemsetAsync(P->Yh.p, 0, P->Yh.bytes(), st));     // std::fill(y, 0) (:1026-1032)
-    for (size_t k = 0; k < P->pull->rows.size(); k++)                          // needs only this rank's own x chunk
-        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, 0, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
-    if (P->ag_pending) { GT_CUDA(cudaStreamWaitEvent(st, ctx->ev_ag, 0)); P->ag_pending = false; }
-    for (size_t k = 0; k < P->pull->rows.size(); k++)
-        if (P->pull->yn[k]) pull_spmv(ctx, P->pull, (uint32_t) k, 1, P->Xh.p, P->Yh.p + P->pull->yoff[k]);
-    if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
-        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, P->pull->ychunk, CT_F64, CO_SUM, st);
+    // Row segments led by other ranks first: their partial y leaves for the leader while the owned segment is computed.
+    // Part 0 needs only this rank's own x chunk, so it runs while the other chunks are still arriving.
+    for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) pull_spmv(ctx, L, (uint32_t) k, 0, x, P->Yh.p + L->yoff[k]);
+    if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 0, x, P->Yh.p + L->yoff[own]);
+    pull_x_arrived(P);
+    for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) pull_spmv(ctx, L, (uint32_t) k, 1, x, P->Yh.p + L->yoff[k]);
+    if (P->wy) {
+        // combine_2d_stationary's follower -> leader sends (:1083-1108) as puts into slot `me` of the leader's window
+        P->y_epoch++;
+        GT_CUDA(cudaEventRecord(P->ev_b, st));
+        GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, P->ev_b, 0));
+        const int G = P->wy->size;
+        for (size_t k = 0; k < R; k++) {
+            if (k == own) continue;
+            const int q = (int) (L->yoff[k] / L->ychunk);                       // group rank of the segment's leader
+            const size_t off = ((size_t) (P->y_epoch & 1) * G + P->wy->me) * L->ychunk * sizeof(double);
+            peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) L->yn[k] * sizeof(double), P->y_epoch, ctx->comm_stream);
+        }
+        GT_CUDA(cudaEventRecord(P->ev_ypush, ctx->comm_stream));
+        P->ypush_pending = true;
+    }
+    if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 1, x, P->Yh.p + L->yoff[own]);
+    if (P->wy) peer_wait_all(ctx, P->wy, P->y_epoch, st);                       // the followers' partials of the owned segment
+    else if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
+        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, L->ychunk, CT_F64, CO_SUM, st);
 }
 
 static void pull_apply(gt_program* P, bool count_active) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
+    const PullLayout* L = P->pull;
     const uint32_t n = P->own_hot->n;
     if (count_active) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (n) {
-        k_pr_apply_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->Yh.p + P->pull->yoff[P->own_row_slot], P->rank_h.p, P->deg_h.p, P->flag_h.p, P->C_h.p,
-                                                                   P->Xh.p + P->pull->xoff[P->own_col_slot], n, P->prm.alpha, P->prm.tol,
+        YParts yr{};
+        if (P->wy)                                    // combine_postprocess_stationary_for_all (:1522-1541): y += y_follower
+            for (int m = 0; m < P->wy->size; m++)
+                if (m != P->wy->me) yr.p[yr.n++] = (const double*) P->wy->local + ((size_t) (P->y_epoch & 1) * P->wy->size + m) * L->ychunk;
+        k_pr_apply_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->Yh.p + L->yoff[P->own_row_slot], yr, P->rank_h.p, P->deg_h.p, P->flag_h.p, P->C_h.p,
+                                                                   pull_x_next(P) + L->xoff[P->own_col_slot], n, P->prm.alpha, P->prm.tol,
                                                                    count_active ? P->d_active.p : nullptr);
         ctx->kernel_launches++;
     }
@@ -692,6 +782,14 @@ extern "C" int gt_program_free(gt_program* p) {
         if (p->h_counts) cudaFreeHost(p->h_counts);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
+        if (p->wx || p->wy) {                     // every put into these windows was consumed before execute() returned
+            cudaStreamSynchronize(p->ctx->comm_stream);
+            cudaStreamSynchronize(p->ctx->stream);
+            gt::peer_window_destroy(p->ctx, p->wx);
+            gt::peer_window_destroy(p->ctx, p->wy);
+        }
+        if (p->ev_b) cudaEventDestroy(p->ev_b);
+        if (p->ev_ypush) cudaEventDestroy(p->ev_ypush);
         delete p;
     });
 }
@@ -770,10 +868,13 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
             } else if (p->iteration >= num_iterations) break;
         }
-        if (p->ag_pending) { GT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ag, 0)); p->ag_pending = false; }
-        if (p->pull) gt::pull_state_out(p);            // hot-order working state -> V (one pass per execute, inside the timed window)
+        if (p->pull) { gt::pull_x_arrived(p); gt::pull_state_out(p); }   // hot-order working state -> V (one pass per execute, inside the timed window)
         GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
+        if (p->wx || p->wy) GT_CUDA(cudaMemcpyAsync(&p->h_active[1], gt::peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, ctx->stream));
         GT_CUDA(cudaStreamSynchronize(ctx->stream));
+        if ((p->wx || p->wy) && (uint32_t) p->h_active[1])
+            throw gt::Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " +
+                                             std::to_string((uint32_t) p->h_active[1] - 1) + " (results are invalid)");
         float ms = 0;
         GT_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         p->tm.execute_ms = ms;
@@ -792,7 +893,7 @@ extern "C" int gt_program_run_phase(gt_program* p, int phase) {
         if (phase == 0) {
             p->x_ready = false;
             gt::scatter_gather(p);
-            if (p->ag_pending) { GT_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ctx->ev_ag, 0)); p->ag_pending = false; }
+            if (p->pull) gt::pull_x_arrived(p);
             GT_CUDA(cudaStreamSynchronize(p->ctx->stream));
         }
         else if (phase == 1) gt::combine(p);

@@ -133,4 +133,7 @@ struct gt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // gt_ctx_timer_*
     cudaStream_t comm_stream = nullptr;         // collectives that overlap compute (x all-gather of the pull path)
     cudaEvent_t ev_x = nullptr, ev_ag = nullptr; // own x chunk written / all-gather landed
+    // NVLink peer exchange (gt_peer.cu): source table of the arrival counters' values, error word, poll timeout
+    gt::DevBuf<uint32_t> peer_seq, peer_err;
+    double peer_timeout_ms = 10000.0;
 };

@@ -1,0 +1,136 @@
+// gt_peer.cu — the x / y exchange of the pull path over NVLink peer memory, without a collective.
+//
+// The reference moves x along the column group with one Ibcast per segment and partial y along the row
+// group with Isend/Irecv to the segment's leader (src/vp/vertex_program.hpp:843-862,970-1013,1083-1108);
+// the first version of this library used one ncclAllGather + one ncclReduceScatter per iteration.  Both
+// are bulk-synchronous: nothing downstream starts before the whole collective has finished on every
+// member, and an NCCL kernel needs SM slots that the persistent SpMV kernel has taken.
+//
+// Here every member of a group owns a WINDOW (one cudaMalloc, exported with cudaIpcGetMemHandle and mapped
+// by the other members).  A producer writes its chunk straight into the consumers' windows with the copy
+// engines (cudaMemcpyAsync to the peer mapping: NVLink 5 through NVSwitch, no SM involved) and then
+// advances a 32-bit arrival counter in the consumer's window with a 4-byte copy on the same stream, so
+// the counter lands after the payload.  A consumer orders its stream behind the counters it needs with a
+// one-warp polling kernel placed exactly where the data is first read.  There is no rendezvous: a rank
+// that is ahead keeps computing, a transfer overlaps whatever kernel is running on either side, and the
+// consumer waits only if the bytes really have not arrived.  Buffers that a fast peer could overwrite
+// while a slow one still reads them are double-buffered by epoch parity (gt_engine.cu).
+#include "gt_peer.h"
+
+namespace gt {
+
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
+}
+
+// lane q polls counter q (16 bytes apart) until (int32)(counter - value) >= 0; `skip` = this rank
+__global__ void k_peer_wait(const uint32_t* flags, int n, int skip, uint32_t value, unsigned long long timeout_ns, uint32_t* err) {
+    const int q = threadIdx.x;
+    if (q < n && q != skip) {
+        const volatile uint32_t* f = flags + 4 * q;
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        while ((int32_t) (*f - value) < 0) {
+            __nanosleep(64);
+            if ((++spins & 1023u) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (!t0) t0 = now;
+                else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 1u + (uint32_t) q); break; }
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+static void ensure_ctx_peer_state(gt_ctx* ctx) {
+    if (ctx->peer_seq.p) return;
+    ctx->peer_seq.alloc(kPeerSeqLen);
+    k_iota<<<256, 256, 0, ctx->stream>>>(ctx->peer_seq.p, kPeerSeqLen);
+    ctx->kernel_launches++;
+    ctx->peer_err.alloc(1);
+    GT_CUDA(cudaMemsetAsync(ctx->peer_err.p, 0, 4, ctx->stream));
+    GT_CUDA(cudaGetLastError());
+    GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (const char* e = getenv("GT_PEER_TIMEOUT_MS")) ctx->peer_timeout_ms = std::max(1.0, atof(e));
+}
+
+uint32_t* peer_error_word(gt_ctx* ctx) { return ctx->peer_err.p; }
+
+PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes) {
+    GT_REQUIRE(ctx->comm, "peer window: needs a multi-rank context");
+    ensure_ctx_peer_state(ctx);
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<PeerWindow> w(new PeerWindow());
+    w->grp = grp;
+    w->size = comm_size_in(ctx->comm, grp);
+    w->me = comm_rank_in(ctx->comm, grp);
+    w->data_bytes = (data_bytes + 255) / 256 * 256;
+    w->total_bytes = w->data_bytes + 16 * (size_t) w->size;
+    w->remote.assign(w->size, nullptr);
+    uint32_t ok = 1;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void**) &w->local, w->total_bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; w->local = nullptr; }
+    if (ok) {
+        GT_CUDA(cudaMemsetAsync(w->local, 0, w->total_bytes, st));
+        if (cudaIpcGetMemHandle(&mine, w->local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // handles of all members, through the group's communicator
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DevBuf<uint8_t> hb; hb.alloc(64 * (size_t) w->size);
+    GT_CUDA(cudaMemcpyAsync(hb.p + 64 * (size_t) w->me, &mine, 64, cudaMemcpyHostToDevice, st));
+    comm_allgather_inplace(ctx->comm, grp, hb.p, 64, CT_U8, st);
+    std::vector<cudaIpcMemHandle_t> all(w->size);
+    GT_CUDA(cudaMemcpyAsync(all.data(), hb.p, 64 * (size_t) w->size, cudaMemcpyDeviceToHost, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    if (ok) w->remote[w->me] = w->local;
+    for (int q = 0; q < w->size && ok; q++) {
+        if (q == w->me) continue;
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        w->remote[q] = (uint8_t*) p;
+    }
+    // all ranks of the job agree (this is also the barrier that orders every member's zero-fill before the first put)
+    DevBuf<uint32_t> d_ok; d_ok.alloc(1);
+    GT_CUDA(cudaMemcpyAsync(d_ok.p, &ok, 4, cudaMemcpyHostToDevice, st));
+    comm_allreduce(ctx->comm, COMM_WORLD, d_ok.p, d_ok.p, 1, CT_U32, CO_MIN, st);
+    uint32_t all_ok = 0;
+    GT_CUDA(cudaMemcpyAsync(&all_ok, d_ok.p, 4, cudaMemcpyDeviceToHost, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    if (!all_ok) {
+        for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
+        if (w->local) cudaFree(w->local);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return w.release();
+}
+
+void peer_window_destroy(gt_ctx* ctx, PeerWindow* w) {
+    if (!w) return;
+    // No rendezvous here: the engine consumes (waits for) every put before execute() / run_phase() returns, so no
+    // transfer targets a window whose owner has reached this point; the mappings are reference-counted by the driver.
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
+    if (w->local) cudaFree(w->local);
+    cudaGetLastError();
+    delete w;
+}
+
+void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value, cudaStream_t s) {
+    GT_REQUIRE(value < kPeerSeqLen, "peer exchange: arrival counter exhausted (re-create the context)");
+    GT_REQUIRE(dst_offset + bytes <= w->data_bytes, "peer exchange: put outside the window");
+    if (bytes) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset, src, bytes, cudaMemcpyDefault, s));
+    GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me), ctx->peer_seq.p + value, 4, cudaMemcpyDefault, s));
+}
+
+void peer_wait_all(gt_ctx* ctx, const PeerWindow* w, uint32_t value, cudaStream_t s) {
+    if (w->size <= 1) return;
+    k_peer_wait<<<1, 32, 0, s>>>(w->flag(w->me, 0), w->size, w->me, value, (unsigned long long) (ctx->peer_timeout_ms * 1e6), ctx->peer_err.p);
+    ctx->kernel_launches++;
+    GT_CUDA(cudaGetLastError());
+}
+
+}  // namespace gt

@@ -1,0 +1,37 @@
+// gt_peer.h — NVLink peer windows: device buffers that every member of a row / column group can write
+// into directly (see gt_peer.cu).
+#pragma once
+#include "gt_internal.h"
+
+namespace gt {
+
+// One device allocation per group member, each mapped into every other member's address space
+// (cudaIpc).  Layout of every member's allocation is the same: `data_bytes` of payload followed by one
+// 32-bit arrival counter per group member (16 bytes apart).
+struct PeerWindow {
+    CommGroup grp = COMM_WORLD;
+    int size = 1, me = 0;
+    size_t data_bytes = 0, total_bytes = 0;
+    uint8_t* local = nullptr;
+    std::vector<uint8_t*> remote;          // [size], remote[me] == local
+    uint32_t* flag(int member, int from) const {              // counter on `member` that `from` advances
+        return (uint32_t*) (remote[member] + data_bytes) + 4 * from;
+    }
+};
+
+// Collective over the WORLD communicator (every rank calls it the same number of times, in the same order);
+// the window itself spans `grp`.  Returns nullptr on every rank if any rank could not map its peers.
+PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes);
+void peer_window_destroy(gt_ctx* ctx, PeerWindow* w);
+
+// dst_member's copy of the window <- local bytes, by copy engine over NVLink, then dst_member's counter
+// for this rank <- value (same stream, so it lands after the payload)
+void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value, cudaStream_t s);
+// blocks `s` (on the device) until every other member's counter in the local window has reached `value`
+void peer_wait_all(gt_ctx* ctx, const PeerWindow* w, uint32_t value, cudaStream_t s);
+// device-side error word: 0, or 1 + the member whose counter did not arrive within the timeout
+uint32_t* peer_error_word(gt_ctx* ctx);
+
+constexpr uint32_t kPeerSeqLen = 1u << 20;   // values a counter can take in the lifetime of a context
+
+}  // namespace gt
