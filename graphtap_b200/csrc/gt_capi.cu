@@ -57,6 +57,8 @@ extern "C" int gt_ctx_destroy(gt_ctx* ctx) {
         cudaSetDevice(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+        for (int i = 1; i < GT_PEER_MAX_LANES; i++)
+            if (ctx->put_stream[i]) { cudaStreamSynchronize(ctx->put_stream[i]); cudaStreamDestroy(ctx->put_stream[i]); }
         gt::comm_destroy(ctx->comm);
         if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
         if (ctx->ev_x) { cudaEventDestroy(ctx->ev_x); cudaEventDestroy(ctx->ev_ag); }

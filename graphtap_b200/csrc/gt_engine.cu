@@ -363,7 +363,7 @@ struct gt_program {
     size_t x_stride = 0;                           // doubles between the two x buffers inside wx
     uint32_t x_epoch = 0, y_epoch = 0;             // puts issued so far (= the value the arrival counters must reach)
     bool x_wait_pending = false, ypush_pending = false, pull_ready = false;
-    cudaEvent_t ev_b = nullptr, ev_ypush = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_yput[GT_PEER_MAX_LANES] = {};   // y complete for the follower segments / their puts have read Yh
     gt::DevBuf<double> rank_h;
     gt::DevBuf<uint32_t> deg_h;
     gt::DevBuf<uint8_t> flag_h, C_h;
@@ -473,7 +473,7 @@ static void pull_alloc(gt_program* P) {
     P->own_hot = &P->g->hot[P->g->hot_of_row_slot[P->own_row_slot]];
     P->rank_h.alloc(P->own_hot->n); P->deg_h.alloc(P->own_hot->n); P->flag_h.alloc(P->own_hot->n); P->C_h.alloc(P->own_hot->n);
     GT_CUDA(cudaEventCreateWithFlags(&P->ev_b, cudaEventDisableTiming));
-    GT_CUDA(cudaEventCreateWithFlags(&P->ev_ypush, cudaEventDisableTiming));
+    for (int i = 0; i < GT_PEER_MAX_LANES; i++) GT_CUDA(cudaEventCreateWithFlags(&P->ev_yput[i], cudaEventDisableTiming));
     P->pull_ready = true;
 }
 
@@ -574,10 +574,11 @@ static void pull_scatter_gather(gt_program* P) {
         // on the side stream, while this rank's SpMV over its own chunk is already running
         P->x_epoch++;
         GT_CUDA(cudaEventRecord(ctx->ev_x, st));
-        GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_x, 0));
+        peer_put_begin(ctx, ctx->ev_x);
         const size_t off = ((size_t) (P->x_epoch & 1) * P->x_stride + P->pull->xoff[P->own_col_slot]) * sizeof(double);
         for (int j = 1; j < P->wx->size; j++)
-            peer_put(ctx, P->wx, (P->wx->me + j) % P->wx->size, off, xo, (size_t) n * sizeof(double), P->x_epoch, ctx->comm_stream);
+            peer_put(ctx, P->wx, (P->wx->me + j) % P->wx->size, off, xo, (size_t) n * sizeof(double), P->x_epoch);
+        peer_put_end(ctx, nullptr);
         P->x_wait_pending = true;
     } else if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
         // the all-gather runs on its own stream; the SpMV over the own chunk does not wait for it
@@ -604,7 +605,7 @@ static void pull_combine(gt_program* P) {
     const double* x = pull_x_cur(P);
     const size_t R = L->rows.size();
     const size_t own = (size_t) P->own_row_slot;
-    if (P->ypush_pending) { GT_CUDA(cudaStreamWaitEvent(st, P->ev_ypush, 0)); P->ypush_pending = false; }   // last put has read Yh
+    if (P->ypush_pending) { peer_puts_done(ctx, P->ev_yput, st); P->ypush_pending = false; }   // the last puts have read Yh
     if (P->Yh.n) GT_CUDA(cudaMemsetAsync(P->Yh.p, 0, P->Yh.bytes(), st));     // std::fill(y, 0) (:1026-1032)
     // Row segments led by other ranks first: their partial y leaves for the leader while the owned segment is computed.
     // Part 0 needs only this rank's own x chunk, so it runs while the other chunks are still arriving.
@@ -616,15 +617,15 @@ static void pull_combine(gt_program* P) {
         // combine_2d_stationary's follower -> leader sends (:1083-1108) as puts into slot `me` of the leader's window
         P->y_epoch++;
         GT_CUDA(cudaEventRecord(P->ev_b, st));
-        GT_CUDA(cudaStreamWaitEvent(ctx->comm_stream, P->ev_b, 0));
+        peer_put_begin(ctx, P->ev_b);
         const int G = P->wy->size;
         for (size_t k = 0; k < R; k++) {
             if (k == own) continue;
             const int q = (int) (L->yoff[k] / L->ychunk);                       // group rank of the segment's leader
             const size_t off = ((size_t) (P->y_epoch & 1) * G + P->wy->me) * L->ychunk * sizeof(double);
-            peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) L->yn[k] * sizeof(double), P->y_epoch, ctx->comm_stream);
+            peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) L->yn[k] * sizeof(double), P->y_epoch);
         }
-        GT_CUDA(cudaEventRecord(P->ev_ypush, ctx->comm_stream));
+        peer_put_end(ctx, P->ev_yput);
         P->ypush_pending = true;
     }
     if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 1, x, P->Yh.p + L->yoff[own]);
@@ -783,13 +784,11 @@ extern "C" int gt_program_free(gt_program* p) {
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
         if (p->wx || p->wy) {                     // every put into these windows was consumed before execute() returned
-            cudaStreamSynchronize(p->ctx->comm_stream);
-            cudaStreamSynchronize(p->ctx->stream);
             gt::peer_window_destroy(p->ctx, p->wx);
             gt::peer_window_destroy(p->ctx, p->wy);
         }
         if (p->ev_b) cudaEventDestroy(p->ev_b);
-        if (p->ev_ypush) cudaEventDestroy(p->ev_ypush);
+        for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (p->ev_yput[i]) cudaEventDestroy(p->ev_yput[i]);
         delete p;
     });
 }

@@ -123,6 +123,7 @@ void comm_allreduce(Comm* c, CommGroup g, const void* send, void* recv, size_t c
 
 }  // namespace gt
 
+#define GT_PEER_MAX_LANES 4
 // ---- the three opaque handle types ------------------------------------------------------------------
 struct gt_ctx {
     int device = 0, rank = 0, nranks = 1;
@@ -133,7 +134,10 @@ struct gt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // gt_ctx_timer_*
     cudaStream_t comm_stream = nullptr;         // collectives that overlap compute (x all-gather of the pull path)
     cudaEvent_t ev_x = nullptr, ev_ag = nullptr; // own x chunk written / all-gather landed
-    // NVLink peer exchange (gt_peer.cu): source table of the arrival counters' values, error word, poll timeout
+    // NVLink peer exchange (gt_peer.cu): source table of the arrival counters' values, error word, poll timeout, and
+    // the streams ("lanes") a put is spread over so that several copy engines drive the links at once
     gt::DevBuf<uint32_t> peer_seq, peer_err;
     double peer_timeout_ms = 10000.0;
+    int peer_lanes = 0;
+    cudaStream_t put_stream[GT_PEER_MAX_LANES] = {};
 };

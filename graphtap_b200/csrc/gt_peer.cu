@@ -23,10 +23,11 @@ __global__ void k_iota(uint32_t* p, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
 
-// lane q polls counter q (16 bytes apart) until (int32)(counter - value) >= 0; `skip` = this rank
+// thread q polls counter q (16 bytes apart; GT_PEER_MAX_LANES counters per member) until
+// (int32)(counter - value) >= 0; `skip` = this rank
 __global__ void k_peer_wait(const uint32_t* flags, int n, int skip, uint32_t value, unsigned long long timeout_ns, uint32_t* err) {
     const int q = threadIdx.x;
-    if (q < n && q != skip) {
+    if (q < n && q / GT_PEER_MAX_LANES != skip) {
         const volatile uint32_t* f = flags + 4 * q;
         unsigned long long t0 = 0;
         unsigned spins = 0;
@@ -36,7 +37,7 @@ __global__ void k_peer_wait(const uint32_t* flags, int n, int skip, uint32_t val
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (!t0) t0 = now;
-                else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 1u + (uint32_t) q); break; }
+                else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 1u + (uint32_t) (q / GT_PEER_MAX_LANES)); break; }
             }
         }
     }
@@ -53,6 +54,11 @@ static void ensure_ctx_peer_state(gt_ctx* ctx) {
     GT_CUDA(cudaGetLastError());
     GT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (const char* e = getenv("GT_PEER_TIMEOUT_MS")) ctx->peer_timeout_ms = std::max(1.0, atof(e));
+    // one copy engine moves ~350 GB/s over NVLink 5 (measured: 105 MB in 0.34 ms); several lanes reach the links' rate
+    ctx->peer_lanes = GT_PEER_MAX_LANES;
+    if (const char* e = getenv("GT_PEER_LANES")) ctx->peer_lanes = std::min(GT_PEER_MAX_LANES, std::max(1, atoi(e)));
+    ctx->put_stream[0] = ctx->comm_stream;
+    for (int i = 1; i < GT_PEER_MAX_LANES; i++) GT_CUDA(cudaStreamCreateWithFlags(&ctx->put_stream[i], cudaStreamNonBlocking));
 }
 
 uint32_t* peer_error_word(gt_ctx* ctx) { return ctx->peer_err.p; }
@@ -65,8 +71,9 @@ PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes) {
     w->grp = grp;
     w->size = comm_size_in(ctx->comm, grp);
     w->me = comm_rank_in(ctx->comm, grp);
+    GT_REQUIRE(w->size * GT_PEER_MAX_LANES <= 1024, "peer window: group too large");
     w->data_bytes = (data_bytes + 255) / 256 * 256;
-    w->total_bytes = w->data_bytes + 16 * (size_t) w->size;
+    w->total_bytes = w->data_bytes + 16 * (size_t) w->size * GT_PEER_MAX_LANES;
     w->remote.assign(w->size, nullptr);
     uint32_t ok = 1;
     cudaIpcMemHandle_t mine;
@@ -111,7 +118,7 @@ void peer_window_destroy(gt_ctx* ctx, PeerWindow* w) {
     if (!w) return;
     // No rendezvous here: the engine consumes (waits for) every put before execute() / run_phase() returns, so no
     // transfer targets a window whose owner has reached this point; the mappings are reference-counted by the driver.
-    cudaStreamSynchronize(ctx->comm_stream);
+    for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (ctx->put_stream[i]) cudaStreamSynchronize(ctx->put_stream[i]);
     cudaStreamSynchronize(ctx->stream);
     for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
     if (w->local) cudaFree(w->local);
@@ -119,16 +126,37 @@ void peer_window_destroy(gt_ctx* ctx, PeerWindow* w) {
     delete w;
 }
 
-void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value, cudaStream_t s) {
+void peer_put_begin(gt_ctx* ctx, cudaEvent_t ready) {
+    for (int i = 0; i < ctx->peer_lanes; i++) GT_CUDA(cudaStreamWaitEvent(ctx->put_stream[i], ready, 0));
+}
+
+void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value) {
     GT_REQUIRE(value < kPeerSeqLen, "peer exchange: arrival counter exhausted (re-create the context)");
     GT_REQUIRE(dst_offset + bytes <= w->data_bytes, "peer exchange: put outside the window");
-    if (bytes) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset, src, bytes, cudaMemcpyDefault, s));
-    GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me), ctx->peer_seq.p + value, 4, cudaMemcpyDefault, s));
+    const int K = ctx->peer_lanes;
+    // small transfers ride on lane 0 alone; every lane still advances its counter, the consumer waits for all of them
+    const size_t slice = bytes < (1u << 20) ? bytes : ((bytes + K - 1) / K + 255) / 256 * 256;
+    for (int i = 0; i < GT_PEER_MAX_LANES; i++) {
+        cudaStream_t s = ctx->put_stream[i < K ? i : 0];
+        const size_t lo = std::min(bytes, (size_t) i * slice), hi = i < K ? std::min(bytes, lo + slice) : lo;
+        if (hi > lo) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset + lo, (const uint8_t*) src + lo, hi - lo, cudaMemcpyDefault, s));
+        GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me, i), ctx->peer_seq.p + value, 4, cudaMemcpyDefault, s));
+    }
+}
+
+void peer_put_end(gt_ctx* ctx, cudaEvent_t* done) {
+    if (!done) return;
+    for (int i = 0; i < ctx->peer_lanes; i++) GT_CUDA(cudaEventRecord(done[i], ctx->put_stream[i]));
+}
+
+void peer_puts_done(gt_ctx* ctx, cudaEvent_t* done, cudaStream_t s) {
+    for (int i = 0; i < ctx->peer_lanes; i++) GT_CUDA(cudaStreamWaitEvent(s, done[i], 0));
 }
 
 void peer_wait_all(gt_ctx* ctx, const PeerWindow* w, uint32_t value, cudaStream_t s) {
     if (w->size <= 1) return;
-    k_peer_wait<<<1, 32, 0, s>>>(w->flag(w->me, 0), w->size, w->me, value, (unsigned long long) (ctx->peer_timeout_ms * 1e6), ctx->peer_err.p);
+    const int n = w->size * GT_PEER_MAX_LANES;
+    k_peer_wait<<<1, (n + 31) / 32 * 32, 0, s>>>(w->flag(w->me, 0, 0), n, w->me, value, (unsigned long long) (ctx->peer_timeout_ms * 1e6), ctx->peer_err.p);
     ctx->kernel_launches++;
     GT_CUDA(cudaGetLastError());
 }
