@@ -54,8 +54,9 @@ static void ensure_ctx_peer_state(gt_ctx* ctx) {
     GT_CUDA(cudaGetLastError());
     GT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (const char* e = getenv("GT_PEER_TIMEOUT_MS")) ctx->peer_timeout_ms = std::max(1.0, atof(e));
-    // one copy engine moves ~350 GB/s over NVLink 5 (measured: 105 MB in 0.34 ms); several lanes reach the links' rate
-    ctx->peer_lanes = GT_PEER_MAX_LANES;
+    // A put can be sliced over several streams ("lanes").  Measured on B200 / NVSwitch: one stream already moves
+    // ~450-500 GB/s per direction and 4 lanes change nothing (profiles/r01_peer_exchange.md), so the default is 1.
+    ctx->peer_lanes = 1;
     if (const char* e = getenv("GT_PEER_LANES")) ctx->peer_lanes = std::min(GT_PEER_MAX_LANES, std::max(1, atoi(e)));
     ctx->put_stream[0] = ctx->comm_stream;
     for (int i = 1; i < GT_PEER_MAX_LANES; i++) GT_CUDA(cudaStreamCreateWithFlags(&ctx->put_stream[i], cudaStreamNonBlocking));
