@@ -303,13 +303,20 @@ PullLayout* pull_build(gt_graph* g) {
     std::unique_ptr<PullLayout> P(new PullLayout());
     const size_t S = g->cols.size(), R = g->rows.size();
     GT_REQUIRE(S <= kPullMaxSegs, "pull layout: too many local column segments");
-    if (const char* e = getenv("GT_PULL_VROW")) P->vrow = std::max(8, atoi(e));
+    bool vrow_fixed = false;
+    if (const char* e = getenv("GT_PULL_VROW")) { P->vrow = std::max(8, atoi(e)); vrow_fixed = true; }
+    if (const char* e = getenv("GT_PULL_BAND")) P->band = (uint32_t) std::max(0, atoi(e));
     if (const char* e = getenv("GT_PULL_L1HOT")) P->l1hot = (uint32_t) std::max(0, atoi(e));
     if (const char* e = getenv("GT_PULL_L2HINT")) P->l2hint = atoi(e) != 0;
     if (const char* e = getenv("GT_PULL_UNROLL")) P->unroll = atoi(e) == 4 ? 4 : 8;
     if (const char* e = getenv("GT_PULL_THREADS")) P->threads = std::min(1024, std::max(32, atoi(e) / 32 * 32));
     if (const char* e = getenv("GT_PULL_CTAS")) P->ctas_per_sm = std::min(8, std::max(1, atoi(e)));
-    const uint32_t kVRow = P->vrow;
+    // A warp's longest slice bounds the tail of a launch, so the virtual-row length follows the launch size: one GPU's
+    // share at p = 8 is 2^25 entries per launch, where 128 beats 512 by 14 % (profiles/r01_sweep_vrow.log).
+    auto vrow_for = [&](uint64_t entries) -> uint32_t {
+        if (vrow_fixed) return P->vrow;
+        return entries < (48ull << 20) ? 128u : entries < (96ull << 20) ? 256u : P->vrow;
+    };
 
     // concatenated x / y spaces (see PullLayout): chunk index = group rank of the segment's leader
     P->xoff.resize(S); P->xn.resize(S); P->yoff.resize(R); P->yn.resize(R);
@@ -388,11 +395,12 @@ PullLayout* pull_build(gt_graph* g) {
             ctx->kernel_launches += 8;
             sorted = db.Current();
         }
-        // own x chunk apart from the rest (multi-GPU only)
+        // own x chunk apart from the rest (multi-GPU), or the hottest `band` columns apart from the tail (GT_PULL_BAND)
         uint64_t* other = (sorted == keys.p) ? alt.p : keys.p;
         uint64_t n_own = 0;
-        if (ctx->comm && comm_size_in(ctx->comm, COMM_COLGRP) > 1) {
-            const uint32_t lo = P->xoff[g->lay.info.accu_segment_col], hi = lo + P->xchunk;
+        const bool multi = ctx->comm && comm_size_in(ctx->comm, COMM_COLGRP) > 1;
+        if (multi || P->band) {
+            const uint32_t lo = multi ? P->xoff[g->lay.info.accu_segment_col] : 0, hi = multi ? lo + P->xchunk : P->band;
             DevBuf<unsigned long long> d_n; d_n.alloc(2);
             size_t tb = 0;
             GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) total, CodeInRange{lo, hi, true}, st));
@@ -407,8 +415,8 @@ PullLayout* pull_build(gt_graph* g) {
             ctx->kernel_launches += 2;
             sorted = other;
         }
-        if (n_own) build_sell(ctx, sorted, n_own, nr, kVRow, pad_code, Q.own);
-        build_sell(ctx, sorted + n_own, total - n_own, nr, kVRow, pad_code, Q.rest);
+        if (n_own) build_sell(ctx, sorted, n_own, nr, vrow_for(n_own), pad_code, Q.own);
+        build_sell(ctx, sorted + n_own, total - n_own, nr, vrow_for(total - n_own), pad_code, Q.rest);
     }
     return P.release();
 }

@@ -36,6 +36,7 @@ struct PullLayout {
     uint32_t ychunk = 0, ylen = 0;
     std::vector<PullRows> rows;                 // per row slot
     uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
+    uint32_t band = 0;                          // single GPU: columns [0, band) of the hot order form a pass of their own (0 = one pass)
     uint32_t l1hot = 0;                         // hottest columns (per rank) gathered L1::evict_last, the rest L1::evict_first; 0 = no distinction
     bool l2hint = true;                         // L2 eviction hints: index stream evict-first, x evict-last (-8 % on RMAT-26)
     int unroll = 8;
