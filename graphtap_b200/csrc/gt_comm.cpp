@@ -7,7 +7,9 @@
 // row group with the reduction done by the leader (:1083-1108,1522-1573), and a world Allreduce for
 // convergence (:1918).  Here those are ONE in-place ncclAllGather (x, column group), ONE in-place
 // ncclReduceScatter (y, row group) and an ncclAllReduce per iteration, on communicators split with the
-// same rank lists (every member of a group leads exactly one of the group's segments).
+// same rank lists (every member of a group leads exactly one of the group's segments).  PageRank's iteration no
+// longer uses them: its x / y exchange runs over NVLink peer windows (gt_peer.cu), NCCL only carries the window
+// handles at start-up; BFS / CC / SSSP and the GT_PEER=0 mode still do.
 //
 // NCCL is bound with dlopen("libnccl.so.2") so that (a) inside a Python process the copy torch already
 // loaded is reused (one NCCL per process), (b) a single-GPU run needs no NCCL at all, and (c) the

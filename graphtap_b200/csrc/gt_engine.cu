@@ -553,6 +553,17 @@ static void pull_state_out(gt_program* P) {
     GT_CUDA(cudaGetLastError());
 }
 
+// ---- PageRank iteration on the pull layout, with the exchange over NVLink peer windows ------------------------------
+// Why two buffers per window are enough (no barrier anywhere in the loop):
+//  * x: a column-group peer Q puts x(k+2) into the parity that held x(k) only after its applicator of iteration k+1,
+//    which needs this rank's x(k+1) for Q's SpMV — and this rank puts x(k+1) only after its own applicator of
+//    iteration k, i.e. after its last read of x(k).  Likewise this rank's applicator overwrites its local copy of the
+//    parity of x(k-1) only after every peer's x(k) has arrived, which they sent after consuming x(k-1).
+//  * y: a row-group peer F puts y(k+2) into the parity of y(k) only after its applicator of iteration k+1, which
+//    needs this rank's partial y(k+1), sent after this rank's applicator of iteration k (stream order) — the reader
+//    of y(k).  One buffer would not do: F's y(k+1) depends on x(k+1) from F's column group, not on this rank.
+//  * every put is consumed (its counter waited for) before execute() / run_phase() returns, so a window is never
+//    written after its owner could have freed it.
 // x buffer the current iteration reads (parity of the last put) / the one the next messenger writes
 static inline double* pull_x_cur(gt_program* P) { return P->xbuf[P->wx ? (P->x_epoch & 1) : 0]; }
 static inline double* pull_x_next(gt_program* P) { return P->xbuf[P->wx ? ((P->x_epoch + 1) & 1) : 0]; }

@@ -23,9 +23,9 @@
 //     profiles/r01_ncu_pull_s26_hot*.txt).  The kernel is bound by the L1-miss -> L2 gather path: one 32-byte
 //     sector per edge, ~280 G gathers/s per GPU (~12.9 TB/s of L2 sector traffic), the structural limit of a
 //     gather design.  L2 eviction hints (index stream evict-first, x evict-last) are worth 8 %.
-//   * Multi-GPU: x is one equal-sized chunk per member of the column group, so the exchange is a single in-place
-//     all-gather; entries whose column lies in this rank's own chunk form a separate SELL array that runs while
-//     the all-gather of the other chunks is in flight.
+//   * Multi-GPU: x is one equal-sized chunk per member of the column group; entries whose column lies in this
+//     rank's own chunk form a separate SELL array that runs while the other chunks are still arriving over NVLink
+//     (copy-engine puts into peer windows, gt_peer.cu; or one in-place all-gather with GT_PEER=0).
 //
 // Results: each row's sum is formed in a fixed order by one lane (split rows excepted), so it differs from
 // the reference's column-order sum only by f64 rounding, ~1e-16 relative — inside the 1e-6 contract.
