@@ -119,6 +119,46 @@ __global__ void __launch_bounds__(1024) k_frontier(const uint32_t* __restrict__ 
     }
 }
 
+// ---- frontier exchange over NVLink peer windows (non-stationary programs) -----------------------------------
+// The reference ships a column segment's x either dense or as the compacted (xi, xv) pair, by the owner's 0.6 rule,
+// with the item count ahead of the payload (:760-784,864-1013).  Here the owner's SMs store straight into the other
+// column-group members' windows: the frontier list if the rule says sparse, the dense segment otherwise, then a
+// header {mode, count} and the arrival counter (gt_peer.cu).  The size never visits the host.
+struct PutTargets { uint32_t* dense[8]; uint32_t* xi[8]; uint32_t* xv[8]; uint32_t* hdr[8]; uint32_t* flag[8]; int n; };
+__device__ __forceinline__ void copy_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nth) {
+    const uint32_t n4 = n >> 2;                    // both sides are 16-byte aligned (chunks are multiples of 4 elements)
+    const uint4* s4 = (const uint4*) src;
+    uint4* d4 = (uint4*) dst;
+    for (uint32_t i = tid; i < n4; i += nth) d4[i] = s4[i];
+    for (uint32_t i = (n4 << 2) + tid; i < n; i += nth) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(256) k_put_frontier(const uint32_t* __restrict__ dense, const uint32_t* __restrict__ xi, const uint32_t* __restrict__ xv,
+                                                       const unsigned int* __restrict__ count, uint32_t n, double ratio, uint32_t* own_hdr,
+                                                       PutTargets T, uint32_t epoch, unsigned int* done) {
+    const unsigned k = *count;
+    const bool sparse = n && ((double) k / (double) n <= ratio);        // :768-772
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int j = 0; j < T.n; j++) {
+        if (sparse) { copy_u32(T.xi[j], xi, k, tid, nth); copy_u32(T.xv[j], xv, k, tid, nth); }
+        else copy_u32(T.dense[j], dense, n, tid, nth);
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;                             // the last CTA to finish publishes: every payload store is ordered before
+    __threadfence_system();
+    if (threadIdx.x == 0) { own_hdr[0] = sparse; own_hdr[1] = k; *done = 0; }
+    if ((int) threadIdx.x < T.n) {
+        volatile uint32_t* h = T.hdr[threadIdx.x];
+        h[0] = sparse; h[1] = k;
+        __threadfence_system();
+        volatile uint32_t* f = T.flag[threadIdx.x];
+        for (int l = 0; l < GT_PEER_MAX_LANES; l++) f[4 * l] = epoch;
+    }
+}
+
 // ---- applicator ------------------------------------------------------------------------------------------
 // stationary, TCSC: rows with I[i] take y[j++] (here y[r] with v = IR[r]) (:1655-1670)
 __global__ void k_apply_f64(VState V, int app, const uint32_t* __restrict__ IR, uint32_t nr, const double* __restrict__ y,
@@ -373,6 +413,14 @@ struct gt_program {
     uint64_t sparse_bytes = 0;                     // bytes_algorithmic bookkeeping of the current iteration
     bool dense_tiles = true;
     std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
+    // non-stationary programs on several GPUs: x segments, frontier lists and {mode, count} headers live in a window
+    // the column-group peers store into (k_put_frontier); xi / xv are the per-slot list pointers either way
+    gt::PeerWindow* wxn = nullptr;
+    std::vector<uint32_t*> xi, xv;
+    std::vector<int> xq;                           // chunk of every x slot = group rank of the segment's leader
+    uint32_t* wxn_hdr = nullptr;                   // [group size][4] inside the local window
+    uint32_t* h_hdr = nullptr;                     // pinned copy of the headers
+    gt::DevBuf<unsigned int> put_done;
     gt::DevBuf<unsigned long long> d_active;      // [0] active count
     gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
     unsigned long long* h_active = nullptr;       // pinned
@@ -422,12 +470,29 @@ static void prog_alloc(gt_program* P) {
         for (const SegMaps& s : *P->prow) P->ychunk = std::max<size_t>(P->ychunk, s.nnz);
         P->xchunk = (P->xchunk + 3) / 4 * 4;           // chunks stay 16-byte aligned for both element sizes
         P->ychunk = (P->ychunk + 3) / 4 * 4;
-        P->Xcat.alloc((P->X.size() * P->xchunk + 1) * P->esize());
+        const size_t S = P->X.size();
+        P->xq.resize(S);
+        for (size_t k = 0; k < S; k++) P->xq[k] = (int) chunk_of(P->bcast_group, (*P->pcol)[k].segment, k);
+        const char* e = getenv("GT_PEER");
+        if (!P->stationary && ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1 && S <= 8 && !(e && atoi(e) == 0))
+            P->wxn = peer_window_create(ctx, P->bcast_group, (3 * S * P->xchunk + 4 * S) * sizeof(uint32_t));
+        uint8_t* xbase;
+        if (P->wxn) {                                  // [dense S x chunk][xi S x chunk][xv S x chunk][headers S x 4]
+            xbase = P->wxn->local;
+            P->wxn_hdr = (uint32_t*) P->wxn->local + 3 * S * P->xchunk;
+            P->put_done.alloc(1);
+            GT_CUDA(cudaMemsetAsync(P->put_done.p, 0, 4, ctx->stream));
+            GT_CUDA(cudaMallocHost((void**) &P->h_hdr, 4 * S * sizeof(uint32_t)));
+            memset(P->h_hdr, 0, 4 * S * sizeof(uint32_t));
+        } else {
+            P->Xcat.alloc((S * P->xchunk + 1) * P->esize());
+            GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, ctx->stream));
+            xbase = P->Xcat.p;
+        }
         P->Ycat.alloc(std::max<size_t>(1, P->Y.size() * P->ychunk) * P->esize());
-        GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, ctx->stream));
         GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, ctx->stream));
-        for (size_t k = 0; k < P->X.size(); k++) {
-            P->X[k].p = P->Xcat.p + chunk_of(P->bcast_group, (*P->pcol)[k].segment, k) * P->xchunk * P->esize();
+        for (size_t k = 0; k < S; k++) {
+            P->X[k].p = xbase + (size_t) P->xq[k] * P->xchunk * P->esize();
             P->X[k].n = (size_t) (*P->pcol)[k].nnz * P->esize();
         }
         for (size_t k = 0; k < P->Y.size(); k++) {
@@ -436,8 +501,17 @@ static void prog_alloc(gt_program* P) {
         }
     }
     if (!P->stationary) {
-        P->XI.resize(P->X.size()); P->XV.resize(P->X.size());
-        for (size_t k = 0; k < P->X.size(); k++) { P->XI[k].alloc((*P->pcol)[k].nnz); P->XV[k].alloc((*P->pcol)[k].nnz); }
+        const size_t S = P->X.size();
+        P->XI.resize(S); P->XV.resize(S); P->xi.resize(S); P->xv.resize(S);
+        for (size_t k = 0; k < S; k++) {
+            if (P->wxn) {
+                P->xi[k] = (uint32_t*) P->wxn->local + (S + P->xq[k]) * P->xchunk;
+                P->xv[k] = (uint32_t*) P->wxn->local + (2 * S + P->xq[k]) * P->xchunk;
+            } else {
+                P->XI[k].alloc((*P->pcol)[k].nnz); P->XV[k].alloc((*P->pcol)[k].nnz);
+                P->xi[k] = P->XI[k].p; P->xv[k] = P->XV[k].p;
+            }
+        }
     }
     P->d_active.alloc(2);
     P->d_counts.alloc(std::max<size_t>(1, P->X.size()));
@@ -675,6 +749,37 @@ static void scatter_gather(gt_program* P) {
         else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
         ctx->kernel_launches++;
     }
+    if (P->wxn) {
+        // scatter_gather_nonstationary + its activity filtering + bcast_nonstationary (:710-784,864-1013): own frontier
+        // list, then sparse-or-dense stores into the column-group peers' windows; the headers of all local segments
+        // come back with the caller's one synchronisation
+        const size_t S = P->X.size();
+        const int me = P->wxn->me, k = P->own_col_slot;
+        GT_CUDA(cudaMemsetAsync(P->d_counts.p, 0, P->d_counts.bytes(), st));
+        if (own.nnz) {
+            k_frontier<<<grid_for((own.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, own.nnz, P->xi[k], P->xv[k], P->d_counts.p + k);
+            ctx->kernel_launches++;
+        }
+        PutTargets T{};
+        for (int j = 1; j < P->wxn->size; j++) {
+            const int q = (me + j) % P->wxn->size;
+            uint32_t* base = (uint32_t*) P->wxn->remote[q];
+            T.dense[T.n] = base + (size_t) me * P->xchunk;
+            T.xi[T.n] = base + (S + me) * P->xchunk;
+            T.xv[T.n] = base + (2 * S + me) * P->xchunk;
+            T.hdr[T.n] = base + 3 * S * P->xchunk + 4 * (size_t) me;
+            T.flag[T.n] = P->wxn->flag(q, me, 0);
+            T.n++;
+        }
+        P->x_epoch++;
+        k_put_frontier<<<2 * ctx->sm_count, 256, 0, st>>>((const uint32_t*) P->X[k].p, P->xi[k], P->xv[k], P->d_counts.p + k, own.nnz, P->activity_filtering_ratio,
+                                                         P->wxn_hdr + 4 * me, T, P->x_epoch, P->put_done.p);
+        ctx->kernel_launches++;
+        peer_wait_all(ctx, P->wxn, P->x_epoch, st);
+        GT_CUDA(cudaMemcpyAsync(P->h_hdr, P->wxn_hdr, 4 * S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaGetLastError());
+        return;
+    }
     if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)      // bcast_stationary / bcast_nonstationary
         comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xcat.p, P->xchunk, P->f64 ? CT_F64 : CT_U32, st);
     if (!P->stationary) {                         // frontier lists + sizes (:754-784); the caller synchronises
@@ -682,7 +787,7 @@ static void scatter_gather(gt_program* P) {
         for (size_t k = 0; k < P->X.size(); k++) {
             const SegMaps& s = (*P->pcol)[k];
             if (!s.nnz) continue;
-            k_frontier<<<grid_for((s.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->XI[k].p, P->XV[k].p, P->d_counts.p + k);
+            k_frontier<<<grid_for((s.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->xi[k], P->xv[k], P->d_counts.p + k);
             ctx->kernel_launches++;
         }
         GT_CUDA(cudaMemcpyAsync(P->h_counts, P->d_counts.p, P->X.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
@@ -706,11 +811,13 @@ static void combine(gt_program* P) {
         if (P->stationary) {
             launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
         } else {
-            const uint32_t k = P->h_counts[xs];
             const uint32_t nx = (*P->pcol)[xs].nnz;
-            const bool sparse = nx && ((double) k / (double) nx <= P->activity_filtering_ratio);   // :768-772
+            uint32_t k;
+            bool sparse;
+            if (P->wxn) { const uint32_t* h = P->h_hdr + 4 * P->xq[xs]; sparse = h[0] != 0; k = h[1]; }   // the owner's decision travels with the data
+            else { k = P->h_counts[xs]; sparse = nx && ((double) k / (double) nx <= P->activity_filtering_ratio); }   // :768-772
             if (sparse) P->sparse_bytes += 16ull * k; else all_sparse = false;
-            if (sparse) { any_sparse = true; launch_spmspv(ctx, g, T, P->semiring, P->XI[xs].p, P->XV[xs].p, k, P->Y[ys].p, nullptr); }
+            if (sparse) { any_sparse = true; launch_spmspv(ctx, g, T, P->semiring, P->xi[xs], P->xv[xs], k, P->Y[ys].p, nullptr); }
             else launch_spmv(ctx, g, T, P->semiring, P->ordering, true, P->X[xs].p, P->Y[ys].p, nullptr);
         }
     }
@@ -794,10 +901,12 @@ extern "C" int gt_program_free(gt_program* p) {
         if (p->h_counts) cudaFreeHost(p->h_counts);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
-        if (p->wx || p->wy) {                     // every put into these windows was consumed before execute() returned
+        if (p->wx || p->wy || p->wxn) {           // every put into these windows was consumed before execute() returned
             gt::peer_window_destroy(p->ctx, p->wx);
             gt::peer_window_destroy(p->ctx, p->wy);
+            gt::peer_window_destroy(p->ctx, p->wxn);
         }
+        if (p->h_hdr) cudaFreeHost(p->h_hdr);
         if (p->ev_b) cudaEventDestroy(p->ev_b);
         for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (p->ev_yput[i]) cudaEventDestroy(p->ev_yput[i]);
         delete p;
@@ -876,13 +985,19 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
                 if (!p->stationary && !p->timing) { gt::scatter_gather(p); sg_done = true; }   // overlaps the wait below
                 p->converged = gt::has_converged_end(p);
                 if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
-            } else if (p->iteration >= num_iterations) break;
+            } else {
+                if (p->iteration >= num_iterations) break;
+                // without the convergence all-reduce nothing orders this rank's next frontier put behind the peers'
+                // reads of the current one (the x window of the non-stationary programs has a single buffer)
+                if (p->wxn) gt::comm_allreduce(ctx->comm, gt::COMM_WORLD, p->d_active.p + 1, p->d_active.p + 1, 1, gt::CT_U64, gt::CO_SUM, ctx->stream);
+            }
         }
         if (p->pull) { gt::pull_x_arrived(p); gt::pull_state_out(p); }   // hot-order working state -> V (one pass per execute, inside the timed window)
         GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
-        if (p->wx || p->wy) GT_CUDA(cudaMemcpyAsync(&p->h_active[1], gt::peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, ctx->stream));
+        const bool peer_used = p->wx || p->wy || p->wxn;
+        if (peer_used) GT_CUDA(cudaMemcpyAsync(&p->h_active[1], gt::peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, ctx->stream));
         GT_CUDA(cudaStreamSynchronize(ctx->stream));
-        if ((p->wx || p->wy) && (uint32_t) p->h_active[1])
+        if (peer_used && (uint32_t) p->h_active[1])
             throw gt::Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " +
                                              std::to_string((uint32_t) p->h_active[1] - 1) + " (results are invalid)");
         float ms = 0;
