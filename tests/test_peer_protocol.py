@@ -198,3 +198,63 @@ def test_one_buffer_is_not(nbuf_x, nbuf_y):
         except Hazard:
             found += 1
     assert found > 0
+
+
+# ---- non-stationary programs: single-buffered frontier window, ordered by the per-iteration all-reduce -----------------
+def run_frontier_model(R, iters, seed, allreduce=True):
+    """One column group of R ranks (graphtap_b200/csrc/gt_engine.cu scatter_gather / combine for BFS, CC, SSSP): per
+    iteration every rank stores its frontier into the peers' windows with a kernel on its only stream, polls the
+    arrival counters, reads all segments in combine, applies, and joins the world all-reduce of the convergence count.
+    The window has ONE buffer; the claim is that the all-reduce makes that safe."""
+    rng = random.Random(seed)
+    win = {r: [Cell() for _ in range(R)] for r in range(R)}          # win[rank][segment]
+    flag = {r: [0] * R for r in range(R)}
+    arrived = [0] * (iters + 2)
+    queues = {r: [] for r in range(R)}
+    always = lambda: True
+    for r in range(R):
+        q = queues[r]
+        for k in range(1, iters + 1):
+            def put_begin(r=r, k=k):
+                for m in range(R):
+                    Sim.write_begin(win[m][r], f"rank {r} frontier put {k} -> {m}")
+
+            def put_end(r=r, k=k):
+                for m in range(R):
+                    Sim.write_end(win[m][r], k)
+                    flag[m][r] = k
+            q.append(("put begin", always, put_begin))
+            q.append(("put end", always, put_end))
+            q.append(("wait", lambda r=r, k=k: all(flag[r][m] >= k for m in range(R)), lambda: None))
+            q.append(("combine begin", always, lambda r=r, k=k: [Sim.read_begin(win[r][m], k, f"rank {r} combine {k}") for m in range(R)]))
+            q.append(("combine end", always, lambda r=r: [Sim.read_end(win[r][m]) for m in range(R)]))
+            if allreduce:
+                q.append(("all-reduce arrive", always, lambda k=k: arrived.__setitem__(k, arrived[k] + 1)))
+                q.append(("all-reduce done", lambda k=k: arrived[k] == R, lambda: None))
+    heads = {r: 0 for r in range(R)}
+    while True:
+        ready = [r for r in range(R) if heads[r] < len(queues[r]) and queues[r][heads[r]][1]()]
+        if not ready:
+            if all(heads[r] == len(queues[r]) for r in range(R)):
+                return
+            raise Hazard("deadlock")
+        r = rng.choice(ready)
+        for _ in range(rng.choice((1, 1, 2, 8, 30))):
+            if heads[r] < len(queues[r]) and queues[r][heads[r]][1]():
+                queues[r][heads[r]][2]()
+                heads[r] += 1
+            else:
+                break
+
+
+@pytest.mark.parametrize("R", [2, 4])
+def test_frontier_window_single_buffer_is_ordered_by_the_allreduce(R):
+    for seed in range(100):
+        run_frontier_model(R, iters=6, seed=seed, allreduce=True)
+    found = 0
+    for seed in range(100):
+        try:
+            run_frontier_model(R, iters=6, seed=seed, allreduce=False)
+        except Hazard:
+            found += 1
+    assert found > 0                     # without it a fast rank overwrites a segment a slow one is still reading
