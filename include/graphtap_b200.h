@@ -68,7 +68,12 @@ typedef struct gt_program gt_program;
  * (src/mpi/env.hpp:77-124,140-157).  nranks > 1 builds a world NCCL communicator from `nccl_id`
  * (128 bytes from gt_nccl_unique_id on rank 0, distributed by the host program) and splits the
  * row-group and column-group communicators from the reference's rank lists
- * (src/mat/matrix.hpp:447-465). */
+ * (src/mat/matrix.hpp:447-465).  The per-iteration exchanges of the reference (Ibcast of x along the column
+ * group, Isend/Irecv of partial y along the row group, src/vp/vertex_program.hpp:843-1013,1083-1108) run as
+ * stores into cudaIpc-mapped NVLink peer windows of the other group members where the ranks are processes of one
+ * node (PageRank: x and y; BFS/CC/SSSP: the sparse-or-dense frontier), and as NCCL collectives otherwise or with
+ * the environment variable GT_PEER=0; the communicators also carry the window handles and the convergence
+ * all-reduce (:1918). */
 GT_API int gt_nccl_unique_id(void* out128);
 GT_API int gt_ctx_create(int device, int rank, int nranks, const void* nccl_id, gt_ctx** out);
 GT_API int gt_ctx_destroy(gt_ctx* ctx);
