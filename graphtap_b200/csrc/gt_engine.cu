@@ -858,9 +858,13 @@ static void has_converged_begin(gt_program* P) {
     }
     if (ctx->comm) comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p, P->d_active.p, 1, CT_U64, CO_SUM, st);
     GT_CUDA(cudaMemcpyAsync(P->h_active, P->d_active.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (P->wxn) GT_CUDA(cudaMemcpyAsync(&P->h_active[1], peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, st));
 }
 static bool has_converged_end(gt_program* P) {
     GT_CUDA(cudaStreamSynchronize(P->ctx->stream));
+    if (P->wxn && (uint32_t) P->h_active[1])        // a frontier that never arrived must not keep the loop spinning on garbage
+        throw Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " +
+                                     std::to_string((uint32_t) P->h_active[1] - 1));
     return P->h_active[0] == 0;
 }
 
