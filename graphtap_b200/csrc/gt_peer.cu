@@ -64,6 +64,14 @@ static void ensure_ctx_peer_state(gt_ctx* ctx) {
 
 uint32_t* peer_error_word(gt_ctx* ctx) { return ctx->peer_err.p; }
 
+static void window_release(PeerWindow* w) {
+    for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
+    if (w->local) cudaFree(w->local);
+    cudaGetLastError();
+    w->local = nullptr;
+    w->remote.assign(w->size, nullptr);
+}
+
 PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes) {
     GT_REQUIRE(ctx->comm, "peer window: needs a multi-rank context");
     ensure_ctx_peer_state(ctx);
@@ -76,41 +84,44 @@ PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes) {
     w->data_bytes = (data_bytes + 255) / 256 * 256;
     w->total_bytes = w->data_bytes + 16 * (size_t) w->size * GT_PEER_MAX_LANES;
     w->remote.assign(w->size, nullptr);
-    uint32_t ok = 1;
-    cudaIpcMemHandle_t mine;
-    memset(&mine, 0, sizeof(mine));
-    if (cudaMalloc((void**) &w->local, w->total_bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; w->local = nullptr; }
-    if (ok) {
-        GT_CUDA(cudaMemsetAsync(w->local, 0, w->total_bytes, st));
-        if (cudaIpcGetMemHandle(&mine, w->local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    }
-    // handles of all members, through the group's communicator
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-    DevBuf<uint8_t> hb; hb.alloc(64 * (size_t) w->size);
-    GT_CUDA(cudaMemcpyAsync(hb.p + 64 * (size_t) w->me, &mine, 64, cudaMemcpyHostToDevice, st));
-    comm_allgather_inplace(ctx->comm, grp, hb.p, 64, CT_U8, st);
-    std::vector<cudaIpcMemHandle_t> all(w->size);
-    GT_CUDA(cudaMemcpyAsync(all.data(), hb.p, 64 * (size_t) w->size, cudaMemcpyDeviceToHost, st));
-    GT_CUDA(cudaStreamSynchronize(st));
-    if (ok) w->remote[w->me] = w->local;
-    for (int q = 0; q < w->size && ok; q++) {
-        if (q == w->me) continue;
-        void* p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
-        w->remote[q] = (uint8_t*) p;
-    }
-    // all ranks of the job agree (this is also the barrier that orders every member's zero-fill before the first put)
-    DevBuf<uint32_t> d_ok; d_ok.alloc(1);
-    GT_CUDA(cudaMemcpyAsync(d_ok.p, &ok, 4, cudaMemcpyHostToDevice, st));
-    comm_allreduce(ctx->comm, COMM_WORLD, d_ok.p, d_ok.p, 1, CT_U32, CO_MIN, st);
-    uint32_t all_ok = 0;
-    GT_CUDA(cudaMemcpyAsync(&all_ok, d_ok.p, 4, cudaMemcpyDeviceToHost, st));
-    GT_CUDA(cudaStreamSynchronize(st));
-    if (!all_ok) {
-        for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
-        if (w->local) cudaFree(w->local);
-        cudaGetLastError();
-        return nullptr;
+    try {
+        uint32_t ok = 1;
+        cudaIpcMemHandle_t mine;
+        memset(&mine, 0, sizeof(mine));
+        if (cudaMalloc((void**) &w->local, w->total_bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; w->local = nullptr; }
+        if (ok) {
+            GT_CUDA(cudaMemsetAsync(w->local, 0, w->total_bytes, st));
+            if (cudaIpcGetMemHandle(&mine, w->local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+        // handles of all members, through the group's communicator
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        DevBuf<uint8_t> hb; hb.alloc(64 * (size_t) w->size);
+        GT_CUDA(cudaMemcpyAsync(hb.p + 64 * (size_t) w->me, &mine, 64, cudaMemcpyHostToDevice, st));
+        comm_allgather_inplace(ctx->comm, grp, hb.p, 64, CT_U8, st);
+        std::vector<cudaIpcMemHandle_t> all(w->size);
+        GT_CUDA(cudaMemcpyAsync(all.data(), hb.p, 64 * (size_t) w->size, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        if (ok) w->remote[w->me] = w->local;
+        for (int q = 0; q < w->size && ok; q++) {
+            if (q == w->me) continue;
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            w->remote[q] = (uint8_t*) p;
+        }
+        // all ranks of the job agree (this is also the barrier that orders every member's zero-fill before the first put)
+        DevBuf<uint32_t> d_ok; d_ok.alloc(1);
+        GT_CUDA(cudaMemcpyAsync(d_ok.p, &ok, 4, cudaMemcpyHostToDevice, st));
+        comm_allreduce(ctx->comm, COMM_WORLD, d_ok.p, d_ok.p, 1, CT_U32, CO_MIN, st);
+        uint32_t all_ok = 0;
+        GT_CUDA(cudaMemcpyAsync(&all_ok, d_ok.p, 4, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        if (!all_ok) {
+            window_release(w.get());
+            return nullptr;
+        }
+    } catch (...) {
+        window_release(w.get());
+        throw;
     }
     return w.release();
 }
@@ -121,9 +132,7 @@ void peer_window_destroy(gt_ctx* ctx, PeerWindow* w) {
     // transfer targets a window whose owner has reached this point; the mappings are reference-counted by the driver.
     for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (ctx->put_stream[i]) cudaStreamSynchronize(ctx->put_stream[i]);
     cudaStreamSynchronize(ctx->stream);
-    for (int q = 0; q < w->size; q++) if (q != w->me && w->remote[q]) cudaIpcCloseMemHandle(w->remote[q]);
-    if (w->local) cudaFree(w->local);
-    cudaGetLastError();
+    window_release(w);
     delete w;
 }
 
