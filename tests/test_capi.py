@@ -75,3 +75,16 @@ def test_edge_list_readers(tmp_path):
     bad.write_text("1 2 3 4\n")
     with pytest.raises(capi.GraphTapError):
         read_edge_list(str(bad), False)
+
+
+def test_every_environment_knob_is_documented():
+    """The library reads its tuning knobs with getenv(); README.md lists every one of them."""
+    import glob
+    import re
+    knobs = set()
+    for path in glob.glob(os.path.join(ROOT, "graphtap_b200", "csrc", "*.c*")):
+        knobs |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(path).read()))
+    assert knobs, "no getenv() found: the pattern is stale"
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    missing = sorted(k for k in knobs if f"`{k}`" not in readme)
+    assert not missing, f"undocumented environment knobs: {missing}"
