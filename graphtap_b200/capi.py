@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gt_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "gt_ctx_destroy": (C.c_int, [C.c_void_p]),
     "gt_ctx_sync": (C.c_int, [C.c_void_p]),
+    "gt_ctx_barrier": (C.c_int, [C.c_void_p]),
     "gt_ctx_timer_begin": (C.c_int, [C.c_void_p]),
     "gt_ctx_timer_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "gt_ctx_stream": (C.c_void_p, [C.c_void_p]),

@@ -97,6 +97,20 @@ extern "C" int gt_ctx_sync(gt_ctx* ctx) {
     });
 }
 
+extern "C" int gt_ctx_barrier(gt_ctx* ctx) {
+    return gt::guarded([&] {
+        GT_REQUIRE(ctx, "gt_ctx_barrier: NULL ctx");
+        GT_CUDA(cudaSetDevice(ctx->device));
+        GT_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        for (int i = 1; i < GT_PEER_MAX_LANES; i++) if (ctx->put_stream[i]) GT_CUDA(cudaStreamSynchronize(ctx->put_stream[i]));
+        if (ctx->comm) {
+            if (!ctx->barrier_word.p) { ctx->barrier_word.alloc(1); GT_CUDA(cudaMemsetAsync(ctx->barrier_word.p, 0, 4, ctx->stream)); }
+            gt::comm_allreduce(ctx->comm, gt::COMM_WORLD, ctx->barrier_word.p, ctx->barrier_word.p, 1, gt::CT_U32, gt::CO_MAX, ctx->stream);
+        }
+        GT_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
 extern "C" void* gt_ctx_stream(gt_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
 
 extern "C" int gt_dev_alloc(gt_ctx* ctx, size_t bytes, void** out) {

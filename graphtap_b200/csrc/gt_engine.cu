@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) k_put_frontier(const uint32_t* __restrict
         h[0] = sparse; h[1] = k;
         __threadfence_system();
         volatile uint32_t* f = T.flag[threadIdx.x];
-        for (int l = 0; l < GT_PEER_MAX_LANES; l++) f[4 * l] = epoch;
+        *f = epoch & (kPeerSeqLen - 1);
     }
 }
 
@@ -768,7 +768,7 @@ static void scatter_gather(gt_program* P) {
             T.xi[T.n] = base + (S + me) * P->xchunk;
             T.xv[T.n] = base + (2 * S + me) * P->xchunk;
             T.hdr[T.n] = base + 3 * S * P->xchunk + 4 * (size_t) me;
-            T.flag[T.n] = P->wxn->flag(q, me, 0);
+            T.flag[T.n] = P->wxn->flag(q, me);
             T.n++;
         }
         P->x_epoch++;

@@ -136,8 +136,8 @@ struct gt_ctx {
     cudaEvent_t ev_x = nullptr, ev_ag = nullptr; // own x chunk written / all-gather landed
     // NVLink peer exchange (gt_peer.cu): source table of the arrival counters' values, error word, poll timeout, and
     // the streams ("lanes") a put is spread over so that several copy engines drive the links at once
-    gt::DevBuf<uint32_t> peer_seq, peer_err;
-    double peer_timeout_ms = 10000.0;
+    gt::DevBuf<uint32_t> peer_seq, peer_err, peer_fence, barrier_word;
+    double peer_timeout_ms = 30000.0;
     int peer_lanes = 0;
     cudaStream_t put_stream[GT_PEER_MAX_LANES] = {};
 };

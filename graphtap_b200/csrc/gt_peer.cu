@@ -23,21 +23,21 @@ __global__ void k_iota(uint32_t* p, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
 
-// thread q polls counter q (16 bytes apart; GT_PEER_MAX_LANES counters per member) until
-// (int32)(counter - value) >= 0; `skip` = this rank
+// thread q polls the counter of group member q (16 bytes apart) until it has reached `value` (modular, gt_peer.h);
+// `skip` = this rank
 __global__ void k_peer_wait(const uint32_t* flags, int n, int skip, uint32_t value, unsigned long long timeout_ns, uint32_t* err) {
     const int q = threadIdx.x;
-    if (q < n && q / GT_PEER_MAX_LANES != skip) {
+    if (q < n && q != skip) {
         const volatile uint32_t* f = flags + 4 * q;
         unsigned long long t0 = 0;
         unsigned spins = 0;
-        while ((int32_t) (*f - value) < 0) {
+        while (!peer_reached(*f, value)) {
             __nanosleep(64);
             if ((++spins & 1023u) == 0) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (!t0) t0 = now;
-                else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 1u + (uint32_t) (q / GT_PEER_MAX_LANES)); break; }
+                else if (now - t0 > timeout_ns) { atomicCAS(err, 0u, 1u + (uint32_t) q); break; }
             }
         }
     }
@@ -51,12 +51,15 @@ static void ensure_ctx_peer_state(gt_ctx* ctx) {
     ctx->kernel_launches++;
     ctx->peer_err.alloc(1);
     GT_CUDA(cudaMemsetAsync(ctx->peer_err.p, 0, 4, ctx->stream));
+    ctx->peer_fence.alloc(1);
+    GT_CUDA(cudaMemsetAsync(ctx->peer_fence.p, 0, 4, ctx->stream));
     GT_CUDA(cudaGetLastError());
     GT_CUDA(cudaStreamSynchronize(ctx->stream));
     if (const char* e = getenv("GT_PEER_TIMEOUT_MS")) ctx->peer_timeout_ms = std::max(1.0, atof(e));
-    // A put can be sliced over several streams ("lanes").  Measured on B200 / NVSwitch: one stream already moves
-    // ~450-500 GB/s per direction and 4 lanes change nothing (profiles/r01_peer_exchange.md), so the default is 1.
-    ctx->peer_lanes = 1;
+    // One put stream per destination (round-robin over `peer_lanes` streams): a single stream moves ~450-500 GB/s per
+    // direction (profiles/r01_peer_exchange.md), and the three puts of a column group at p = 8 queued behind each other
+    // on it; on separate streams they are driven by different copy engines at the same time.
+    ctx->peer_lanes = GT_PEER_MAX_LANES;
     if (const char* e = getenv("GT_PEER_LANES")) ctx->peer_lanes = std::min(GT_PEER_MAX_LANES, std::max(1, atoi(e)));
     ctx->put_stream[0] = ctx->comm_stream;
     for (int i = 1; i < GT_PEER_MAX_LANES; i++) GT_CUDA(cudaStreamCreateWithFlags(&ctx->put_stream[i], cudaStreamNonBlocking));
@@ -80,9 +83,9 @@ PeerWindow* peer_window_create(gt_ctx* ctx, CommGroup grp, size_t data_bytes) {
     w->grp = grp;
     w->size = comm_size_in(ctx->comm, grp);
     w->me = comm_rank_in(ctx->comm, grp);
-    GT_REQUIRE(w->size * GT_PEER_MAX_LANES <= 1024, "peer window: group too large");
+    GT_REQUIRE(w->size <= 1024, "peer window: group too large");
     w->data_bytes = (data_bytes + 255) / 256 * 256;
-    w->total_bytes = w->data_bytes + 16 * (size_t) w->size * GT_PEER_MAX_LANES;
+    w->total_bytes = w->data_bytes + 16 * (size_t) w->size;
     w->remote.assign(w->size, nullptr);
     try {
         uint32_t ok = 1;
@@ -141,17 +144,11 @@ void peer_put_begin(gt_ctx* ctx, cudaEvent_t ready) {
 }
 
 void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value) {
-    GT_REQUIRE(value < kPeerSeqLen, "peer exchange: arrival counter exhausted (re-create the context)");
     GT_REQUIRE(dst_offset + bytes <= w->data_bytes, "peer exchange: put outside the window");
-    const int K = ctx->peer_lanes;
-    // small transfers ride on lane 0 alone; every lane still advances its counter, the consumer waits for all of them
-    const size_t slice = bytes < (1u << 20) ? bytes : ((bytes + K - 1) / K + 255) / 256 * 256;
-    for (int i = 0; i < GT_PEER_MAX_LANES; i++) {
-        cudaStream_t s = ctx->put_stream[i < K ? i : 0];
-        const size_t lo = std::min(bytes, (size_t) i * slice), hi = i < K ? std::min(bytes, lo + slice) : lo;
-        if (hi > lo) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset + lo, (const uint8_t*) src + lo, hi - lo, cudaMemcpyDefault, s));
-        GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me, i), ctx->peer_seq.p + value, 4, cudaMemcpyDefault, s));
-    }
+    const int d = (dst_member - w->me - 1 + w->size) % w->size;          // 0 .. size-2: which of my destinations this is
+    cudaStream_t s = ctx->put_stream[d % ctx->peer_lanes];
+    if (bytes) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset, src, bytes, cudaMemcpyDefault, s));
+    GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me), ctx->peer_seq.p + (value & (kPeerSeqLen - 1)), 4, cudaMemcpyDefault, s));
 }
 
 void peer_put_end(gt_ctx* ctx, cudaEvent_t* done) {
@@ -165,10 +162,16 @@ void peer_puts_done(gt_ctx* ctx, cudaEvent_t* done, cudaStream_t s) {
 
 void peer_wait_all(gt_ctx* ctx, const PeerWindow* w, uint32_t value, cudaStream_t s) {
     if (w->size <= 1) return;
-    const int n = w->size * GT_PEER_MAX_LANES;
-    k_peer_wait<<<1, (n + 31) / 32 * 32, 0, s>>>(w->flag(w->me, 0, 0), n, w->me, value, (unsigned long long) (ctx->peer_timeout_ms * 1e6), ctx->peer_err.p);
+    const int n = w->size;
+    k_peer_wait<<<1, (n + 31) / 32 * 32, 0, s>>>(w->flag(w->me, 0), n, w->me, value, (unsigned long long) (ctx->peer_timeout_ms * 1e6), ctx->peer_err.p);
     ctx->kernel_launches++;
     GT_CUDA(cudaGetLastError());
+}
+
+void peer_fence_world(gt_ctx* ctx, cudaStream_t s) {
+    if (!ctx->comm) return;
+    ensure_ctx_peer_state(ctx);
+    comm_allreduce(ctx->comm, COMM_WORLD, ctx->peer_fence.p, ctx->peer_fence.p, 1, CT_U32, CO_MAX, s);
 }
 
 }  // namespace gt

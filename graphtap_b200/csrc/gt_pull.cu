@@ -239,6 +239,42 @@ k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__
     }
 }
 
+// Hot-band variant (single GPU, GT_PULL_BAND + GT_PULL_BAND_SMEM=1): the band's x values [0, band) are staged in
+// shared memory once per CTA and every gather of the pass is an LDS; the cold pass keeps the whole L1 for its misses
+// (the kernel that mixed both starved L1, profiles/r01_ncu_pull_s26_hot*.txt).  Codes >= band are padding (0.0).
+template <int UNROLL>
+__global__ void __launch_bounds__(kPullThreads)
+k_spmv_pull_sell_smem(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
+                      const uint32_t* __restrict__ vtgt, uint32_t nv, const double* __restrict__ x, uint32_t band, double* __restrict__ y) {
+    extern __shared__ double xs[];
+    for (uint32_t i = threadIdx.x; i < band; i += blockDim.x) xs[i] = x[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint64_t pol_idx = l2_policy_evict_first();
+    for (uint32_t s = warp; s < nslices; s += nwarps) {
+        const uint64_t base = slice_ptr[s];
+        const uint32_t L = (uint32_t) ((slice_ptr[s + 1] - base) >> 5);
+        const uint32_t* p = sell + base + lane;
+        double acc = 0.0;
+        uint32_t k = 0;
+        for (; k + UNROLL <= L; k += UNROLL) {
+            uint32_t c[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) c[u] = ld_index<true>(p + (uint64_t) (k + u) * 32, pol_idx);
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) acc += c[u] < band ? xs[c[u]] : 0.0;
+        }
+        for (; k < L; k++) { const uint32_t c = ld_index<true>(p + (uint64_t) k * 32, pol_idx); acc += c < band ? xs[c] : 0.0; }
+        const uint32_t v = s * 32 + lane;
+        if (v < nv) {
+            const uint32_t t = vtgt[v];
+            if (t & kPullSplit) atomicAdd(y + (t & ~kPullSplit), acc);
+            else y[t] = acc;
+        }
+    }
+}
+
 struct CodeInRange {                            // column code (hot flag masked) inside [lo, hi)
     uint32_t lo, hi; bool want;
     __device__ bool operator()(const uint64_t& k) const {
@@ -341,9 +377,12 @@ PullLayout* pull_build(gt_graph* g) {
     bool vrow_fixed = false;
     if (const char* e = getenv("GT_PULL_VROW")) { P->vrow = std::max(8, atoi(e)); vrow_fixed = true; }
     if (const char* e = getenv("GT_PULL_BAND")) P->band = (uint32_t) std::max(0, atoi(e));
+    if (const char* e = getenv("GT_PULL_BAND_SMEM")) P->band_smem = atoi(e) != 0;
+    GT_REQUIRE(!P->band_smem || (P->band && P->band <= 28000), "pull layout: GT_PULL_BAND_SMEM needs 0 < GT_PULL_BAND <= 28000 (224 KB of f64)");
+    const bool verbose = getenv("GT_PULL_VERBOSE") && atoi(getenv("GT_PULL_VERBOSE"));
     if (const char* e = getenv("GT_PULL_SPLIT_MIN")) P->split_min = (uint32_t) std::max(0, atoi(e));
-    GT_REQUIRE(!P->split_min || !P->l1hot, "pull layout: GT_PULL_SPLIT_MIN needs GT_PULL_L1HOT=0 (column codes without the hot flag)");
     if (const char* e = getenv("GT_PULL_L1HOT")) P->l1hot = (uint32_t) std::max(0, atoi(e));
+    GT_REQUIRE(!P->split_min || !P->l1hot, "pull layout: GT_PULL_SPLIT_MIN needs GT_PULL_L1HOT=0 (column codes without the hot flag)");
     if (const char* e = getenv("GT_PULL_L2HINT")) P->l2hint = atoi(e) != 0;
     if (const char* e = getenv("GT_PULL_UNROLL")) P->unroll = atoi(e) == 4 ? 4 : 8;
     if (const char* e = getenv("GT_PULL_THREADS")) P->threads = std::min(1024, std::max(32, atoi(e) / 32 * 32));
@@ -472,6 +511,12 @@ PullLayout* pull_build(gt_graph* g) {
         }
         if (n_own) build_sell(ctx, sorted, n_own, nr, vrow_for(n_own), pad_code, Q.own);
         build_sell(ctx, sorted + n_own, total - n_own, nr, vrow_for(total - n_own), pad_code, Q.rest, P->split_min ? has_own.p : nullptr);
+        if (verbose)
+            fprintf(stderr, "[gt pull] rank %d row slot %zu: rows %u entries %llu | part0 entries %llu (%.1f %%) vrows %u slices %u sell_len %llu (pad %.1f %%) | "
+                            "part1 entries %llu vrows %u slices %u sell_len %llu (pad %.1f %%)\n", ctx->rank, k, nr, (unsigned long long) total,
+                    (unsigned long long) Q.own.nnz, 100.0 * Q.own.nnz / total, Q.own.nv, Q.own.nslices, (unsigned long long) Q.own.sell_len,
+                    Q.own.sell_len ? 100.0 * (Q.own.sell_len - Q.own.nnz) / Q.own.sell_len : 0.0, (unsigned long long) Q.rest.nnz, Q.rest.nv, Q.rest.nslices,
+                    (unsigned long long) Q.rest.sell_len, Q.rest.sell_len ? 100.0 * (Q.rest.sell_len - Q.rest.nnz) / Q.rest.sell_len : 0.0);
     }
     return P.release();
 }
@@ -485,6 +530,18 @@ void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, co
     const PullSell& Q = part == 0 ? R.own : R.rest;
     const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : 0;
     if (!Q.nslices) return;
+    if (part == 0 && P->band_smem) {                  // hot band from shared memory: one CTA per SM, the whole carve-out
+        const size_t smem = (size_t) P->band * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            GT_CUDA(cudaFuncSetAttribute(k_spmv_pull_sell_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        k_spmv_pull_sell_smem<8><<<ctx->sm_count, kPullThreads, smem, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, P->band, y);
+        ctx->kernel_launches++;
+        GT_CUDA(cudaGetLastError());
+        return;
+    }
     const int grid = ctx->sm_count * P->ctas_per_sm;
 #define GT_PULL_LAUNCH(U, A, B, C) k_spmv_pull_sell<U, A, B, C><<<grid, P->threads, 0, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, y)
 #define GT_PULL_AB(U, A, B) do { if (accum == 2) GT_PULL_LAUNCH(U, A, B, 2); else if (accum) GT_PULL_LAUNCH(U, A, B, 1); else GT_PULL_LAUNCH(U, A, B, 0); } while (0)

@@ -42,6 +42,7 @@ struct PullLayout {
     // that are long enough to amortise a second y access are touched twice.
     uint32_t split_min = 0;
     uint32_t band = 0;                          // single GPU: columns [0, band) of the hot order form a pass of their own (0 = one pass)
+    bool band_smem = false;                     // GT_PULL_BAND_SMEM: that pass gathers from a shared-memory copy of x[0, band)
     uint32_t l1hot = 0;                         // hottest columns (per rank) gathered L1::evict_last, the rest L1::evict_first; 0 = no distinction
     bool l2hint = true;                         // L2 eviction hints: index stream evict-first, x evict-last (-8 % on RMAT-26)
     int unroll = 8;

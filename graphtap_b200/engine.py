@@ -77,9 +77,7 @@ class Env:
     @classmethod
     def barrier(cls) -> None:
         if cls.ctx is not None:
-            check(lib().gt_ctx_sync(cls.ctx))
-        if cls._dist is not None:
-            cls._dist.barrier()
+            check(lib().gt_ctx_barrier(cls.ctx))          # Env::barrier = MPI_Barrier on the world (src/mpi/env.hpp:164-166)
 
     @classmethod
     def finalize(cls) -> None:

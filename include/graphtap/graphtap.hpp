@@ -26,6 +26,10 @@
 #include <thread>
 #include <type_traits>
 #include <vector>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <ctime>
 #include <unistd.h>
 #include "../graphtap_b200.h"
 
@@ -48,26 +52,53 @@ class Env {
         nranks = n ? atoi(n) : 1;
         is_master = rank == 0;
         unsigned char id[128] = {0};
-        if (nranks > 1) {                          // rank 0 publishes the NCCL id, the others wait for it
-            std::string path = getenv("GT_NCCL_ID_FILE") ? getenv("GT_NCCL_ID_FILE")
-                                                         : "/tmp/gt_nccl_id." + std::string(getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+        std::string id_path;
+        if (nranks > 1) {
+            // Rank 0 publishes the 128-byte NCCL id in a 0600 file inside a private 0700 directory; the name carries the
+            // launcher's job identity (GT_JOB_ID, else TORCHELASTIC_RUN_ID + MASTER_PORT).  A file older than this
+            // process minus the launch skew is a leftover of an earlier job and is never accepted; rank 0 removes the
+            // file before publishing and again once the communicator exists (every rank has read it by then).
+            id_path = nccl_id_path();
+            const time_t born = ::time(nullptr);
             if (rank == 0) {
+                ::unlink(id_path.c_str());
                 if (gt_nccl_unique_id(id)) fail("gt_nccl_unique_id");
-                std::ofstream f(path + ".tmp", std::ios::binary);
-                f.write((const char*) id, 128);
-                f.close();
-                std::rename((path + ".tmp").c_str(), path.c_str());
+                const std::string tmp = id_path + ".tmp." + std::to_string((long) getpid());
+                const int fd = ::open(tmp.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0600);
+                if (fd < 0 || ::write(fd, id, 128) != 128) { fprintf(stderr, "graphtap_b200: cannot publish the NCCL id in %s\n", tmp.c_str()); std::exit(1); }
+                ::close(fd);
+                if (std::rename(tmp.c_str(), id_path.c_str())) { fprintf(stderr, "graphtap_b200: cannot publish the NCCL id in %s\n", id_path.c_str()); std::exit(1); }
             } else {
-                for (int tries = 0; tries < 6000; tries++) {
-                    std::ifstream f(path, std::ios::binary);
-                    if (f && f.read((char*) id, 128)) break;
-                    std::this_thread::sleep_for(std::chrono::milliseconds(10));
+                bool got = false;
+                const double limit_s = getenv("GT_NCCL_ID_TIMEOUT_S") ? atof(getenv("GT_NCCL_ID_TIMEOUT_S")) : 120.0;
+                for (double waited = 0; waited < limit_s && !got; waited += 0.01) {
+                    struct stat sb;
+                    if (::stat(id_path.c_str(), &sb) == 0 && sb.st_size == 128 && sb.st_uid == ::geteuid() && sb.st_mtime + 30 >= born) {
+                        std::ifstream f(id_path, std::ios::binary);
+                        got = f && f.read((char*) id, 128);
+                    }
+                    if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(10));
                 }
+                if (!got) { fprintf(stderr, "graphtap_b200: rank %d never saw the NCCL id of this job in %s\n", rank, id_path.c_str()); std::exit(1); }
             }
         }
         if (gt_ctx_create(l ? atoi(l) : 0, rank, nranks, nranks > 1 ? id : nullptr, &ctx)) fail("gt_ctx_create");
+        if (nranks > 1 && rank == 0) ::unlink(id_path.c_str());
     }
-    static void barrier() { if (ctx) gt_ctx_sync(ctx); }
+    static std::string nccl_id_path() {
+        if (const char* f = getenv("GT_NCCL_ID_FILE")) return f;
+        std::string dir = std::string(getenv("XDG_RUNTIME_DIR") ? getenv("XDG_RUNTIME_DIR") : "/tmp") + "/graphtap_b200." + std::to_string((long) ::geteuid());
+        ::mkdir(dir.c_str(), 0700);
+        struct stat sb;
+        if (::stat(dir.c_str(), &sb) || !S_ISDIR(sb.st_mode) || sb.st_uid != ::geteuid() || (sb.st_mode & 077)) {
+            fprintf(stderr, "graphtap_b200: %s is not a private directory of this user\n", dir.c_str());
+            std::exit(1);
+        }
+        auto env = [](const char* k, const char* d) { const char* v = getenv(k); return std::string(v ? v : d); };
+        return dir + "/nccl_id." + env("GT_JOB_ID", env("TORCHELASTIC_RUN_ID", "job").c_str()) + "." + env("MASTER_PORT", "0");
+    }
+    // Env::barrier (src/mpi/env.hpp:164-166): MPI_Barrier on the world
+    static void barrier() { if (ctx && gt_ctx_barrier(ctx)) fail("gt_ctx_barrier"); }
     static void finalize() { if (ctx) { gt_ctx_destroy(ctx); ctx = nullptr; } }
     static void exit(int code) { finalize(); std::exit(code); }
     static double clock() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -82,6 +82,9 @@ GT_API int gt_ctx_destroy(gt_ctx* ctx);
 GT_API int gt_ctx_timer_begin(gt_ctx* ctx);
 GT_API int gt_ctx_timer_end(gt_ctx* ctx, double* elapsed_ms);
 GT_API int gt_ctx_sync(gt_ctx* ctx);                      /* cudaStreamSynchronize on the engine stream */
+/* Env::barrier (src/mpi/env.hpp:164-166, MPI_Barrier on the world): drains this rank's streams and returns only
+ * when every rank of the job has done the same (a 1-element all-reduce over the world communicator). */
+GT_API int gt_ctx_barrier(gt_ctx* ctx);
 GT_API void* gt_ctx_stream(gt_ctx* ctx);                  /* the cudaStream_t every kernel is launched on */
 /* device scratch the caller may use for staging (cudaMalloc / cudaFree / copies on the ctx stream) */
 GT_API int gt_dev_alloc(gt_ctx* ctx, size_t bytes, void** out);

@@ -193,11 +193,25 @@ def rmat_edges(scale: int, nedges: int | None = None, seed: int | None = None, w
     return out
 
 
-def write_rmat(path: str, scale: int, seed: int | None = None, weighted: bool = False, chunk: int = 1 << 24) -> int:
+def write_rmat(path: str, scale: int, seed: int | None = None, weighted: bool = False, chunk: int = 1 << 22, threads: int | None = None) -> int:
+    """Writes the reference's headerless binary edge file (src/ds/triple.hpp:9-18).  The generator is a ctypes call
+    (the GIL is released), so chunks are produced by a thread pool and written at their offsets."""
+    from concurrent.futures import ThreadPoolExecutor
     n = 16 << scale
-    with open(path, "wb") as f:
-        for first in range(0, n, chunk):
-            rmat_edges(scale, min(chunk, n - first), seed, weighted, first).tofile(f)
+    rec = 12 if weighted else 8
+    lib()
+    fd = os.open(path, os.O_CREAT | os.O_WRONLY | os.O_TRUNC, 0o600)
+    try:
+        os.ftruncate(fd, n * rec)
+
+        def work(first):
+            a = rmat_edges(scale, min(chunk, n - first), seed, weighted, first)
+            os.pwrite(fd, a.tobytes() if not a.flags.c_contiguous else memoryview(a).cast("B"), first * rec)
+
+        with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 1)) as ex:
+            list(ex.map(work, range(0, n, chunk)))
+    finally:
+        os.close(fd)
     return n
 
 
