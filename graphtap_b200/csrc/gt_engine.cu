@@ -20,9 +20,7 @@
 // active (:760-784,970-1013).  On NVLink the dense u32 segment is cheap, so x always travels dense and
 // every rank rebuilds the frontier list locally; the 0.6 rule still picks SpMSpV vs dense SpMV per
 // column segment (:1475), so `sparse_iterations` matches the reference's schedule.
-#include "gt_kernels.cuh"
-#include "gt_pull.h"
-#include "gt_peer.h"
+#include "gt_program.h"
 #include <cub/cub.cuh>
 #include <memory>
 #include <algorithm>
@@ -30,21 +28,6 @@
 #include <chrono>
 
 namespace gt {
-
-static inline int grid_for(uint64_t n, int block, int sm_count, int per_sm = 8) {
-    uint64_t g = (n + block - 1) / block;
-    uint64_t cap = (uint64_t) sm_count * per_sm;
-    return (int) std::max<uint64_t>(1, std::min(g, cap));
-}
-
-// ---- vertex state, SoA on the device (the reference's AoS std::vector<Vertex_State> V is produced on
-// demand by gt_program_state_to_host) --------------------------------------------------------------
-struct VState {
-    double* rank;        // PR
-    uint32_t* a;         // Deg/PR degree | BFS parent | CC label | SSSP distance
-    uint32_t* b;         // BFS hops
-    uint8_t* C;          // activity / convergence flags (:161)
-};
 
 __global__ void k_init_state(VState V, int app, uint32_t th, uint32_t vid0, uint32_t root, double alpha, int stationary) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
@@ -64,11 +47,6 @@ __global__ void k_init_state(VState V, int app, uint32_t th, uint32_t vid0, uint
     }
 }
 
-template <typename T>
-__global__ void k_fill(T* p, T v, uint64_t n) {
-    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) p[i] = v;
-}
-
 // ---- messenger ---------------------------------------------------------------------------------------
 // stationary: x[j] = messenger(V[JC[j]]) over the owned segment's non-empty columns (:699-705)
 __global__ void k_messenger_f64(VState V, int app, const uint32_t* __restrict__ JC, uint32_t nc, double* __restrict__ x) {
@@ -79,86 +57,6 @@ __global__ void k_messenger_f64(VState V, int app, const uint32_t* __restrict__ 
         x[j] = d ? V.rank[v] / (double) d : 0.0;                                           // pr.h:31-33
     }
 }
-// non-stationary: x[j] = C[v] ? messenger(V[v]) : infinity() (:737-751)
-__global__ void k_messenger_u32(VState V, int app, uint32_t vid0, const uint32_t* __restrict__ JC, uint32_t nc, uint32_t* __restrict__ x) {
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
-        const uint32_t v = JC[j];
-        uint32_t m = GT_INF_U32;
-        if (V.C[v]) m = (app == GT_APP_BFS) ? vid0 + v : V.a[v];                            // bfs.h:52-54, cc.h:37-39, sssp.h:45-47
-        x[j] = m;
-    }
-}
-// frontier list of one x segment: xi = compressed ids with x != INF, xv = their values (:744-748); order inside
-// the list is irrelevant to a min reduction.  One atomic per CTA per 4096 elements (block scan of the per-thread
-// counts), not per warp: with millions of active columns per-warp atomics on one counter cost 0.3 ms a pass.
-__global__ void __launch_bounds__(1024) k_frontier(const uint32_t* __restrict__ x, uint32_t nc, uint32_t* __restrict__ xi, uint32_t* __restrict__ xv,
-                                                    unsigned int* __restrict__ count) {
-    typedef cub::BlockScan<unsigned, 1024> BS;
-    __shared__ typename BS::TempStorage tmp;
-    __shared__ unsigned base_s;
-    const uint32_t per_iter = 1024 * 4;
-    for (uint32_t start = blockIdx.x * per_iter; start < nc; start += gridDim.x * per_iter) {
-        const uint32_t j0 = start + threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = (j0 + u < nc) ? x[j0 + u] : GT_INF_U32;
-        unsigned mine = 0;
-#pragma unroll
-        for (int u = 0; u < 4; u++) mine += v[u] != GT_INF_U32;
-        unsigned off, total;
-        BS(tmp).ExclusiveSum(mine, off, total);
-        if (threadIdx.x == 0 && total) base_s = atomicAdd(count, total);
-        __syncthreads();
-        if (total) {
-            unsigned pos = base_s + off;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (v[u] != GT_INF_U32) { xi[pos] = j0 + u; xv[pos] = v[u]; pos++; }
-        }
-        __syncthreads();
-    }
-}
-
-// ---- frontier exchange over NVLink peer windows (non-stationary programs) -----------------------------------
-// The reference ships a column segment's x either dense or as the compacted (xi, xv) pair, by the owner's 0.6 rule,
-// with the item count ahead of the payload (:760-784,864-1013).  Here the owner's SMs store straight into the other
-// column-group members' windows: the frontier list if the rule says sparse, the dense segment otherwise, then a
-// header {mode, count} and the arrival counter (gt_peer.cu).  The size never visits the host.
-struct PutTargets { uint32_t* dense[8]; uint32_t* xi[8]; uint32_t* xv[8]; uint32_t* hdr[8]; uint32_t* flag[8]; int n; };
-__device__ __forceinline__ void copy_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n, uint32_t tid, uint32_t nth) {
-    const uint32_t n4 = n >> 2;                    // both sides are 16-byte aligned (chunks are multiples of 4 elements)
-    const uint4* s4 = (const uint4*) src;
-    uint4* d4 = (uint4*) dst;
-    for (uint32_t i = tid; i < n4; i += nth) d4[i] = s4[i];
-    for (uint32_t i = (n4 << 2) + tid; i < n; i += nth) dst[i] = src[i];
-}
-__global__ void __launch_bounds__(256) k_put_frontier(const uint32_t* __restrict__ dense, const uint32_t* __restrict__ xi, const uint32_t* __restrict__ xv,
-                                                       const unsigned int* __restrict__ count, uint32_t n, double ratio, uint32_t* own_hdr,
-                                                       PutTargets T, uint32_t epoch, unsigned int* done) {
-    const unsigned k = *count;
-    const bool sparse = n && ((double) k / (double) n <= ratio);        // :768-772
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (int j = 0; j < T.n; j++) {
-        if (sparse) { copy_u32(T.xi[j], xi, k, tid, nth); copy_u32(T.xv[j], xv, k, tid, nth); }
-        else copy_u32(T.dense[j], dense, n, tid, nth);
-    }
-    __threadfence_system();
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;                             // the last CTA to finish publishes: every payload store is ordered before
-    __threadfence_system();
-    if (threadIdx.x == 0) { own_hdr[0] = sparse; own_hdr[1] = k; *done = 0; }
-    if ((int) threadIdx.x < T.n) {
-        volatile uint32_t* h = T.hdr[threadIdx.x];
-        h[0] = sparse; h[1] = k;
-        __threadfence_system();
-        volatile uint32_t* f = T.flag[threadIdx.x];
-        *f = epoch & (kPeerSeqLen - 1);
-    }
-}
-
 // ---- applicator ------------------------------------------------------------------------------------------
 // stationary, TCSC: rows with I[i] take y[j++] (here y[r] with v = IR[r]) (:1655-1670)
 __global__ void k_apply_f64(VState V, int app, const uint32_t* __restrict__ IR, uint32_t nr, const double* __restrict__ y,
@@ -177,33 +75,6 @@ __global__ void k_apply_f64(VState V, int app, const uint32_t* __restrict__ IR, 
 __global__ void k_clear_C_empty(uint8_t* C, const uint8_t* __restrict__ I, uint32_t th) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
         if (!I[i]) C[i] = 0;
-}
-// non-stationary, on the rows of rowgrp_nnz_rows (:1739-1751,1768-1780); iteration 0 additionally clears
-// C on the empty rows (:1726-1738,1754-1767) through k_clear_C_empty.  Counts the active vertices.
-__global__ void __launch_bounds__(256) k_apply_u32(VState V, int app, int weighted, const uint32_t* __restrict__ IR, uint32_t nr,
-                                                    const uint32_t* __restrict__ y, uint32_t iteration, unsigned long long* __restrict__ active) {
-    unsigned local = 0;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
-        const uint32_t v = IR[r];
-        const uint32_t yy = y[r];
-        bool ch = false;
-        if (app == GT_APP_BFS) {                                   // bfs.h:65-77
-            if (V.b[v] == GT_INF_U32 && yy != GT_INF_U32) { V.b[v] = iteration + 1; V.a[v] = yy; ch = true; }
-        } else if (app == GT_APP_CC) {                             // cc.h:51-55
-            const uint32_t old = V.a[v];
-            if (yy < old) { V.a[v] = yy; ch = true; }
-        } else {                                                   // sssp.h:58-66
-            const uint32_t old = V.a[v];
-            const uint32_t nw = (yy < old) ? (weighted ? yy : yy + 1) : old;
-            if (nw != old) { V.a[v] = nw; ch = true; }
-        }
-        V.C[v] = ch;
-        local += ch;
-    }
-    typedef cub::BlockReduce<unsigned, 256> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const unsigned tot = BR(tmp).Sum(local);
-    if (threadIdx.x == 0 && tot) atomicAdd(active, (unsigned long long) tot);
 }
 __global__ void __launch_bounds__(256) k_count_u8(const uint8_t* __restrict__ C, uint32_t n, unsigned long long* __restrict__ out) {
     unsigned local = 0;
@@ -364,82 +235,11 @@ static void launch_spmspv(gt_ctx* ctx, const gt_graph* g, const Tile& T, int sem
 
 }  // namespace gt
 
-// ---------------------------------------------------------------------------------------------------------
-struct gt_program {
-    gt_graph* g = nullptr;
-    gt_ctx* ctx = nullptr;
-    int app = 0, stationary = 0, gather_depends_on_apply = 0, apply_depends_on_iter = 0, ordering = GT_ROW;
-    gt_params prm{};
-    int semiring = 0;
-    bool f64 = false;
-    uint32_t th = 0, vid0 = 0;
-    // program-level views: under GT_COL "rows" are the matrix's column groups (:279-325)
-    std::vector<gt::SegMaps>* prow = nullptr;
-    std::vector<gt::SegMaps>* pcol = nullptr;
-    int own_row_slot = 0, own_col_slot = 0;
-    gt::CommGroup bcast_group = gt::COMM_COLGRP, reduce_group = gt::COMM_ROWGRP;
-    // state
-    gt::DevBuf<double> rank;
-    gt::DevBuf<uint32_t> a, b;
-    gt::DevBuf<uint8_t> C;
-    struct Span { uint8_t* p = nullptr; size_t n = 0; };
-    gt::DevBuf<uint8_t> Xcat;                      // all local x segments back to back + one trailing zero element
-    std::vector<Span> X;                           // views into Xcat, |x|*esize bytes each
-    gt::DevBuf<uint8_t> Ycat;                      // all local y segments, same chunking along the row group
-    std::vector<Span> Y;                           // views into Ycat, |y|*esize bytes each
-    size_t xchunk = 0, ychunk = 0;                 // chunk sizes in elements
-    int pr_layout = 1;                             // 1: derived pull layout for the plus-times SpMV (gt_pull.cu), 0: push over TCSC
-    const gt::PullLayout* pull = nullptr;          // owned by the graph
-    // pull mode: x / y in hot order, and the owned segment's state in hot order while execute() runs
-    gt::DevBuf<double> Xh;                         // concatenated hot-ordered x of the local column segments (+ one 0.0)
-    gt::DevBuf<double> Yh;                         // concatenated y chunks of the local row segments
-    // NVLink peer exchange (gt_peer.cu).  wx: the members of the column group put their x chunk into each other's
-    // window, two buffers alternating by epoch parity (a rank one iteration ahead writes x(k+1) while a slower one
-    // still reads x(k)).  wy: followers put the partial y of a row segment into its leader's window, one slot per
-    // sender, again two parities.  Without a window the same exchange is one ncclAllGather / ncclReduceScatter.
-    gt::PeerWindow* wx = nullptr;
-    gt::PeerWindow* wy = nullptr;
-    double* xbuf[2] = {nullptr, nullptr};          // the x buffer of each parity (both = Xh.p without wx)
-    size_t x_stride = 0;                           // doubles between the two x buffers inside wx
-    uint32_t x_epoch = 0, y_epoch = 0;             // puts issued so far (= the value the arrival counters must reach)
-    bool x_wait_pending = false, ypush_pending = false, pull_ready = false;
-    cudaEvent_t ev_b = nullptr, ev_yput[GT_PEER_MAX_LANES] = {};   // y complete for the follower segments / their puts have read Yh
-    gt::DevBuf<double> rank_h;
-    gt::DevBuf<uint32_t> deg_h;
-    gt::DevBuf<uint8_t> flag_h, C_h;
-    const gt::HotOrder* own_hot = nullptr;
-    gt::DevBuf<uint32_t> stage;                    // AoS staging of V for gt_program_state_{to,from}_host (kept: no malloc per call)
-    bool hot_valid = false, x_ready = false, ag_pending = false;
-    uint64_t sparse_bytes = 0;                     // bytes_algorithmic bookkeeping of the current iteration
-    bool dense_tiles = true;
-    std::vector<gt::DevBuf<uint32_t>> XI, XV;      // frontier lists per x slot
-    // non-stationary programs on several GPUs: x segments, frontier lists and {mode, count} headers live in a window
-    // the column-group peers store into (k_put_frontier); xi / xv are the per-slot list pointers either way
-    gt::PeerWindow* wxn = nullptr;
-    std::vector<uint32_t*> xi, xv;
-    std::vector<int> xq;                           // chunk of every x slot = group rank of the segment's leader
-    uint32_t* wxn_hdr = nullptr;                   // [group size][4] inside the local window
-    uint32_t* h_hdr = nullptr;                     // pinned copy of the headers
-    gt::DevBuf<unsigned int> put_done;
-    gt::DevBuf<unsigned long long> d_active;      // [0] active count
-    gt::DevBuf<unsigned int> d_counts;            // frontier size per x slot
-    unsigned long long* h_active = nullptr;       // pinned
-    unsigned int* h_counts = nullptr;             // pinned
-    bool initialized = false, converged = false, empty_cleared = false;
-    uint32_t iteration = 0;
-    double activity_filtering_ratio = 0.6;
-    bool timing = false;
-    gt_timing tm{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-
-    gt::VState vs() { return gt::VState{rank.p, a.p, b.p, C.p}; }
-    size_t esize() const { return f64 ? 8 : 4; }
-};
-
 namespace gt {
 
 static void prog_alloc(gt_program* P) {
     gt_graph* g = P->g;
+    gt_ctx* ctx = P->ctx;
     P->th = g->lay.info.tile_height;
     P->vid0 = (uint32_t) g->lay.info.owned_segment * P->th;
     if (P->ordering == GT_ROW) {
@@ -455,71 +255,39 @@ static void prog_alloc(gt_program* P) {
     P->a.alloc(P->th);
     if (P->app == GT_APP_BFS) P->b.alloc(P->th);
     P->C.alloc(P->th);
+    P->d_active.alloc(4);
+    GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, P->d_active.bytes(), ctx->stream));
+    GT_CUDA(cudaMallocHost((void**) &P->h_active, 4 * sizeof(unsigned long long)));
+    memset(P->h_active, 0, 4 * sizeof(unsigned long long));
+    GT_CUDA(cudaEventCreate(&P->ev0));
+    GT_CUDA(cudaEventCreate(&P->ev1));
+    if (!P->stationary) { ns_alloc(P); return; }          // BFS / CC / SSSP: gt_ns.cu
     P->X.resize(P->pcol->size());
     P->Y.resize(P->prow->size());
     // x: one equal-sized chunk per member of the broadcast group, chunk q = the segment led by group rank q, so the
     // whole exchange is ONE in-place ncclAllGather (the reference: one Ibcast per segment, :843-862,970-1013); y: the
     // same along the reduce group with ONE in-place ncclReduceScatter (the reference: Isend to the leader + host-side
     // combine, :1083-1108,1522-1573).  Every member leads exactly one of its group's segments (tests/test_layout.py).
-    {
-        gt_ctx* ctx = P->ctx;
-        auto chunk_of = [&](CommGroup grp, int segment, size_t k) {
-            return ctx->comm ? (size_t) comm_index_of_world_rank(ctx->comm, grp, g->lay.leader_ranks[segment]) : k;
-        };
-        for (const SegMaps& s : *P->pcol) P->xchunk = std::max<size_t>(P->xchunk, s.nnz);
-        for (const SegMaps& s : *P->prow) P->ychunk = std::max<size_t>(P->ychunk, s.nnz);
-        P->xchunk = (P->xchunk + 3) / 4 * 4;           // chunks stay 16-byte aligned for both element sizes
-        P->ychunk = (P->ychunk + 3) / 4 * 4;
-        const size_t S = P->X.size();
-        P->xq.resize(S);
-        for (size_t k = 0; k < S; k++) P->xq[k] = (int) chunk_of(P->bcast_group, (*P->pcol)[k].segment, k);
-        const char* e = getenv("GT_PEER");
-        if (!P->stationary && ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1 && S <= 8 && !(e && atoi(e) == 0))
-            P->wxn = peer_window_create(ctx, P->bcast_group, (3 * S * P->xchunk + 4 * S) * sizeof(uint32_t));
-        uint8_t* xbase;
-        if (P->wxn) {                                  // [dense S x chunk][xi S x chunk][xv S x chunk][headers S x 4]
-            xbase = P->wxn->local;
-            P->wxn_hdr = (uint32_t*) P->wxn->local + 3 * S * P->xchunk;
-            P->put_done.alloc(1);
-            GT_CUDA(cudaMemsetAsync(P->put_done.p, 0, 4, ctx->stream));
-            GT_CUDA(cudaMallocHost((void**) &P->h_hdr, 4 * S * sizeof(uint32_t)));
-            memset(P->h_hdr, 0, 4 * S * sizeof(uint32_t));
-        } else {
-            P->Xcat.alloc((S * P->xchunk + 1) * P->esize());
-            GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, ctx->stream));
-            xbase = P->Xcat.p;
-        }
-        P->Ycat.alloc(std::max<size_t>(1, P->Y.size() * P->ychunk) * P->esize());
-        GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, ctx->stream));
-        for (size_t k = 0; k < S; k++) {
-            P->X[k].p = xbase + (size_t) P->xq[k] * P->xchunk * P->esize();
-            P->X[k].n = (size_t) (*P->pcol)[k].nnz * P->esize();
-        }
-        for (size_t k = 0; k < P->Y.size(); k++) {
-            P->Y[k].p = P->Ycat.p + chunk_of(P->reduce_group, (*P->prow)[k].segment, k) * P->ychunk * P->esize();
-            P->Y[k].n = (size_t) (*P->prow)[k].nnz * P->esize();
-        }
+    auto chunk_of = [&](CommGroup grp, int segment, size_t k) {
+        return ctx->comm ? (size_t) comm_index_of_world_rank(ctx->comm, grp, g->lay.leader_ranks[segment]) : k;
+    };
+    for (const SegMaps& s : *P->pcol) P->xchunk = std::max<size_t>(P->xchunk, s.nnz);
+    for (const SegMaps& s : *P->prow) P->ychunk = std::max<size_t>(P->ychunk, s.nnz);
+    P->xchunk = (P->xchunk + 3) / 4 * 4;           // chunks stay 16-byte aligned
+    P->ychunk = (P->ychunk + 3) / 4 * 4;
+    const size_t S = P->X.size();
+    P->Xcat.alloc((S * P->xchunk + 1) * P->esize());
+    GT_CUDA(cudaMemsetAsync(P->Xcat.p, 0, P->Xcat.n, ctx->stream));
+    P->Ycat.alloc(std::max<size_t>(1, P->Y.size() * P->ychunk) * P->esize());
+    GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, ctx->stream));
+    for (size_t k = 0; k < S; k++) {
+        P->X[k].p = P->Xcat.p + chunk_of(P->bcast_group, (*P->pcol)[k].segment, k) * P->xchunk * P->esize();
+        P->X[k].n = (size_t) (*P->pcol)[k].nnz * P->esize();
     }
-    if (!P->stationary) {
-        const size_t S = P->X.size();
-        P->XI.resize(S); P->XV.resize(S); P->xi.resize(S); P->xv.resize(S);
-        for (size_t k = 0; k < S; k++) {
-            if (P->wxn) {
-                P->xi[k] = (uint32_t*) P->wxn->local + (S + P->xq[k]) * P->xchunk;
-                P->xv[k] = (uint32_t*) P->wxn->local + (2 * S + P->xq[k]) * P->xchunk;
-            } else {
-                P->XI[k].alloc((*P->pcol)[k].nnz); P->XV[k].alloc((*P->pcol)[k].nnz);
-                P->xi[k] = P->XI[k].p; P->xv[k] = P->XV[k].p;
-            }
-        }
+    for (size_t k = 0; k < P->Y.size(); k++) {
+        P->Y[k].p = P->Ycat.p + chunk_of(P->reduce_group, (*P->prow)[k].segment, k) * P->ychunk * P->esize();
+        P->Y[k].n = (size_t) (*P->prow)[k].nnz * P->esize();
     }
-    P->d_active.alloc(2);
-    P->d_counts.alloc(std::max<size_t>(1, P->X.size()));
-    GT_CUDA(cudaMallocHost((void**) &P->h_active, 2 * sizeof(unsigned long long)));
-    P->h_active[0] = P->h_active[1] = 0;
-    GT_CUDA(cudaMallocHost((void**) &P->h_counts, std::max<size_t>(1, P->X.size()) * sizeof(unsigned int)));
-    GT_CUDA(cudaEventCreate(&P->ev0));
-    GT_CUDA(cudaEventCreate(&P->ev1));
 }
 
 // x / y of the pull path.  Multi-GPU: windows the other group members write into over NVLink (GT_PEER=0 or a failed
@@ -557,11 +325,7 @@ static void prog_initialize(gt_program* P) {
     cudaStream_t st = ctx->stream;
     k_init_state<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->th, P->vid0, P->prm.root, P->prm.alpha, P->stationary);
     ctx->kernel_launches++;
-    if (!P->stationary) {                       // Y starts at infinity() (:625-635)
-        const uint64_t n = P->Ycat.n / 4;
-        k_fill<uint32_t><<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((uint32_t*) P->Ycat.p, GT_INF_U32, n);
-        ctx->kernel_launches++;
-    }
+    if (!P->stationary) ns_initialize(P);       // Y starts at infinity() (:625-635)
     GT_CUDA(cudaGetLastError());
     // PageRank's plus-times SpMV runs as a pull over the derived layout (gt_pull.cu) unless pr_layout = 0
     P->pull = nullptr;
@@ -744,54 +508,11 @@ static void scatter_gather(gt_program* P) {
     cudaStream_t st = ctx->stream;
     const SegMaps& own = (*P->pcol)[P->own_col_slot];
     if (own.nnz) {
-        const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        if (P->f64) k_messenger_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (double*) P->X[P->own_col_slot].p);
-        else k_messenger_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, (uint32_t*) P->X[P->own_col_slot].p);
+        k_messenger_f64<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (double*) P->X[P->own_col_slot].p);
         ctx->kernel_launches++;
     }
-    if (P->wxn) {
-        // scatter_gather_nonstationary + its activity filtering + bcast_nonstationary (:710-784,864-1013): own frontier
-        // list, then sparse-or-dense stores into the column-group peers' windows; the headers of all local segments
-        // come back with the caller's one synchronisation
-        const size_t S = P->X.size();
-        const int me = P->wxn->me, k = P->own_col_slot;
-        GT_CUDA(cudaMemsetAsync(P->d_counts.p, 0, P->d_counts.bytes(), st));
-        if (own.nnz) {
-            k_frontier<<<grid_for((own.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, own.nnz, P->xi[k], P->xv[k], P->d_counts.p + k);
-            ctx->kernel_launches++;
-        }
-        PutTargets T{};
-        for (int j = 1; j < P->wxn->size; j++) {
-            const int q = (me + j) % P->wxn->size;
-            uint32_t* base = (uint32_t*) P->wxn->remote[q];
-            T.dense[T.n] = base + (size_t) me * P->xchunk;
-            T.xi[T.n] = base + (S + me) * P->xchunk;
-            T.xv[T.n] = base + (2 * S + me) * P->xchunk;
-            T.hdr[T.n] = base + 3 * S * P->xchunk + 4 * (size_t) me;
-            T.flag[T.n] = P->wxn->flag(q, me);
-            T.n++;
-        }
-        P->x_epoch++;
-        k_put_frontier<<<2 * ctx->sm_count, 256, 0, st>>>((const uint32_t*) P->X[k].p, P->xi[k], P->xv[k], P->d_counts.p + k, own.nnz, P->activity_filtering_ratio,
-                                                         P->wxn_hdr + 4 * me, T, P->x_epoch, P->put_done.p);
-        ctx->kernel_launches++;
-        peer_wait_all(ctx, P->wxn, P->x_epoch, st);
-        GT_CUDA(cudaMemcpyAsync(P->h_hdr, P->wxn_hdr, 4 * S * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        GT_CUDA(cudaGetLastError());
-        return;
-    }
-    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)      // bcast_stationary / bcast_nonstationary
-        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xcat.p, P->xchunk, P->f64 ? CT_F64 : CT_U32, st);
-    if (!P->stationary) {                         // frontier lists + sizes (:754-784); the caller synchronises
-        GT_CUDA(cudaMemsetAsync(P->d_counts.p, 0, P->d_counts.bytes(), st));
-        for (size_t k = 0; k < P->X.size(); k++) {
-            const SegMaps& s = (*P->pcol)[k];
-            if (!s.nnz) continue;
-            k_frontier<<<grid_for((s.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>((const uint32_t*) P->X[k].p, s.nnz, P->xi[k], P->xv[k], P->d_counts.p + k);
-            ctx->kernel_launches++;
-        }
-        GT_CUDA(cudaMemcpyAsync(P->h_counts, P->d_counts.p, P->X.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    }
+    if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1)      // bcast_stationary (:843-862)
+        comm_allgather_inplace(ctx->comm, P->bcast_group, P->Xcat.p, P->xchunk, CT_F64, st);
     GT_CUDA(cudaGetLastError());
 }
 
@@ -800,31 +521,17 @@ static void combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     gt_graph* g = P->g;
-    if (P->stationary) GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, st));     // std::fill(y, 0) (:1026-1032)
-    bool any_sparse = false, all_sparse = !P->stationary;
+    GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, st));     // std::fill(y, 0) (:1026-1032)
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
     for (const Tile& T : g->tiles) {
         const uint32_t xs = (P->ordering == GT_ROW) ? T.col_slot : T.row_slot;
         const uint32_t ys = (P->ordering == GT_ROW) ? T.row_slot : T.col_slot;
         if (!T.nnz) continue;
-        if (P->stationary) {
-            launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
-        } else {
-            const uint32_t nx = (*P->pcol)[xs].nnz;
-            uint32_t k;
-            bool sparse;
-            if (P->wxn) { const uint32_t* h = P->h_hdr + 4 * P->xq[xs]; sparse = h[0] != 0; k = h[1]; }   // the owner's decision travels with the data
-            else { k = P->h_counts[xs]; sparse = nx && ((double) k / (double) nx <= P->activity_filtering_ratio); }   // :768-772
-            if (sparse) P->sparse_bytes += 16ull * k; else all_sparse = false;
-            if (sparse) { any_sparse = true; launch_spmspv(ctx, g, T, P->semiring, P->xi[xs], P->xv[xs], k, P->Y[ys].p, nullptr); }
-            else launch_spmv(ctx, g, T, P->semiring, P->ordering, true, P->X[xs].p, P->Y[ys].p, nullptr);
-        }
+        launch_spmv(ctx, g, T, P->semiring, P->ordering, false, P->X[xs].p, P->Y[ys].p, nullptr);
     }
-    if (any_sparse) P->tm.sparse_iterations++;
-    P->dense_tiles = !all_sparse;
     if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
-        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Ycat.p, P->ychunk, P->f64 ? CT_F64 : CT_U32, P->f64 ? CO_SUM : CO_MIN, st);
+        comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Ycat.p, P->ychunk, CT_F64, CO_SUM, st);
 }
 
 static void apply(gt_program* P, bool count_active = false) {
@@ -837,11 +544,8 @@ static void apply(gt_program* P, bool count_active = false) {
         ctx->kernel_launches++;
         P->empty_cleared = true;
     }
-    if (!P->stationary) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (own.nnz) {
-        const int grid = grid_for(own.nnz, 256, ctx->sm_count);
-        if (P->f64) k_apply_f64<<<grid, 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
-        else k_apply_u32<<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, own.ids.p, own.nnz, (const uint32_t*) P->Y[P->own_row_slot].p, P->iteration, P->d_active.p);
+        k_apply_f64<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
         ctx->kernel_launches++;
     }
     GT_CUDA(cudaGetLastError());
@@ -851,20 +555,16 @@ static void apply(gt_program* P, bool count_active = false) {
 static void has_converged_begin(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
-    if (P->stationary && !P->pull) {
+    if (!P->pull) {
         GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
         k_count_u8<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, P->th, P->d_active.p);
         ctx->kernel_launches++;
     }
     if (ctx->comm) comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p, P->d_active.p, 1, CT_U64, CO_SUM, st);
     GT_CUDA(cudaMemcpyAsync(P->h_active, P->d_active.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    if (P->wxn) GT_CUDA(cudaMemcpyAsync(&P->h_active[1], peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, st));
 }
 static bool has_converged_end(gt_program* P) {
     GT_CUDA(cudaStreamSynchronize(P->ctx->stream));
-    if (P->wxn && (uint32_t) P->h_active[1])        // a frontier that never arrived must not keep the loop spinning on garbage
-        throw Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " +
-                                     std::to_string((uint32_t) P->h_active[1] - 1));
     return P->h_active[0] == 0;
 }
 
@@ -880,9 +580,8 @@ extern "C" int gt_program_create(gt_graph* g, int app, int stationary, int gathe
         const bool want_stationary = (app == GT_APP_DEG || app == GT_APP_PR);
         GT_REQUIRE((stationary != 0) == want_stationary, "gt_program_create: this app's stationary flag differs from the reference driver's");
         if (ordering == GT_COL && !stationary)
-            throw gt::Error(GT_ERR_UNSUPPORTED, "gt_program_create: _COL_ ordering is provided for stationary programs only (no shipped app uses it otherwise)");
-        if (app == GT_APP_SSSP && !g->weighted)
-            throw gt::Error(GT_ERR_UNSUPPORTED, "gt_program_create: SSSP needs the weighted (HAS_WEIGHT) graph, as built by the reference Makefile:27-28");
+            throw gt::Error(GT_ERR_UNSUPPORTED, "gt_program_create: _COL_ ordering exists for stationary programs only — the reference's spmv_nonstationary has no "
+                                                "_COL_ branch either (src/vp/vertex_program.hpp:1437-1506), it would index y by row ids with the vectors swapped");
         GT_CUDA(cudaSetDevice(g->ctx->device));
         std::unique_ptr<gt_program> P(new gt_program());
         P->g = g; P->ctx = g->ctx; P->app = app; P->stationary = stationary;
@@ -901,16 +600,14 @@ extern "C" int gt_program_free(gt_program* p) {
     return gt::guarded([&] {
         if (!p) return;
         cudaSetDevice(p->ctx->device);
+        gt::ns_free(p);
         if (p->h_active) cudaFreeHost(p->h_active);
-        if (p->h_counts) cudaFreeHost(p->h_counts);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
-        if (p->wx || p->wy || p->wxn) {           // every put into these windows was consumed before execute() returned
+        if (p->wx || p->wy) {                     // every put into these windows was consumed before execute() returned
             gt::peer_window_destroy(p->ctx, p->wx);
             gt::peer_window_destroy(p->ctx, p->wy);
-            gt::peer_window_destroy(p->ctx, p->wxn);
         }
-        if (p->h_hdr) cudaFreeHost(p->h_hdr);
         if (p->ev_b) cudaEventDestroy(p->ev_b);
         for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (p->ev_yput[i]) cudaEventDestroy(p->ev_yput[i]);
         delete p;
@@ -925,6 +622,7 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         else if (n == "timing") p->timing = value != 0;
         else if (n == "iteration") { p->iteration = (uint32_t) value; p->converged = false; }   // public member, vertex_program.hpp:60
         else if (n == "pr_layout") { p->pr_layout = (int) value; p->initialized = false; }
+        else if (n == "bfs_bottom_up_ratio") p->bfs_bottom_up_ratio = value;
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
 }
@@ -947,63 +645,60 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
     return gt::guarded([&] {
         GT_REQUIRE(p, "gt_program_execute: NULL program");
         gt_ctx* ctx = p->ctx;
+        if (p->poisoned)
+            throw gt::Error(GT_ERR_NCCL, "gt_program_execute: an earlier peer exchange of this program timed out; free it and create a new one");
         GT_CUDA(cudaSetDevice(ctx->device));
         if (!p->initialized) gt::prog_initialize(p);
         const bool check = num_iterations == 0;
         const uint64_t launches0 = ctx->kernel_launches;
-        const uint64_t dense_bytes = gt::algorithmic_bytes_dense(p);
         p->tm.bytes_algorithmic = 0;
         p->tm.sparse_iterations = 0;
         const uint32_t it0 = p->iteration;
         GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         p->tm.scatter_gather_ms = p->tm.combine_ms = p->tm.apply_ms = 0;
-        // -DTIMING counters of the reference (:640-684,1018-1054,1611-1637): wall clock around each phase with
-        // the stream drained, only when the "timing" knob is on (it serialises host and device)
-        auto phase = [&](double& acc, auto&& fn) {
-            if (!p->timing) { fn(); return; }
-            GT_CUDA(cudaStreamSynchronize(ctx->stream));
-            const auto t0 = std::chrono::steady_clock::now();
-            fn();
-            GT_CUDA(cudaStreamSynchronize(ctx->stream));
-            acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        };
-        // Non-stationary programs need two numbers on the host per iteration: the frontier sizes (to pick SpMSpV vs
-        // SpMV per column segment, :1475) and the active count (convergence).  The next iteration's scatter_gather is
-        // enqueued BEFORE waiting for the active count, so both arrive with a single stream synchronisation.
-        bool sg_done = false;
-        while (true) {
-            if (!sg_done) {
+        if (!p->stationary) {
+            gt::ns_execute(p, num_iterations);            // records ev1, drains the stream
+        } else {
+            const uint64_t dense_bytes = gt::algorithmic_bytes_dense(p);
+            const bool peer_used = p->wx || p->wy;
+            // the members of a group may enter execute() far apart (one still building its pull layout): meet once, on the
+            // device, before the first arrival counter is polled, so the poll timeout only ever measures a real stall
+            if (peer_used) gt::peer_fence_world(ctx, ctx->stream);
+            // -DTIMING counters of the reference (:640-684,1018-1054,1611-1637): wall clock around each phase with
+            // the stream drained, only when the "timing" knob is on (it serialises host and device)
+            auto phase = [&](double& acc, auto&& fn) {
+                if (!p->timing) { fn(); return; }
+                GT_CUDA(cudaStreamSynchronize(ctx->stream));
+                const auto t0 = std::chrono::steady_clock::now();
+                fn();
+                GT_CUDA(cudaStreamSynchronize(ctx->stream));
+                acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            };
+            while (true) {
                 phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
-                if (!p->stationary) GT_CUDA(cudaStreamSynchronize(ctx->stream));      // h_counts
+                phase(p->tm.combine_ms, [&] { gt::combine(p); });
+                phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
+                p->iteration++;
+                p->tm.bytes_algorithmic += dense_bytes;   // every stationary iteration moves the full structure
+                if (check) {
+                    gt::has_converged_begin(p);
+                    p->converged = gt::has_converged_end(p);
+                    if (p->converged) break;              // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
+                } else if (p->iteration >= num_iterations) break;
             }
-            sg_done = false;
-            p->sparse_bytes = 0; p->dense_tiles = true;
-            phase(p->tm.combine_ms, [&] { gt::combine(p); });
-            phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
-            p->iteration++;
-            // dense iterations move the full structure; an iteration whose tiles all took the
-            // frontier branch is counted at its lower bound (xi/xv + JA pairs of the k frontier columns)
-            p->tm.bytes_algorithmic += p->dense_tiles ? dense_bytes : p->sparse_bytes;
-            if (check) {
-                gt::has_converged_begin(p);
-                if (!p->stationary && !p->timing) { gt::scatter_gather(p); sg_done = true; }   // overlaps the wait below
-                p->converged = gt::has_converged_end(p);
-                if (p->converged) break;          // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
-            } else {
-                if (p->iteration >= num_iterations) break;
-                // without the convergence all-reduce nothing orders this rank's next frontier put behind the peers'
-                // reads of the current one (the x window of the non-stationary programs has a single buffer)
-                if (p->wxn) gt::comm_allreduce(ctx->comm, gt::COMM_WORLD, p->d_active.p + 1, p->d_active.p + 1, 1, gt::CT_U64, gt::CO_SUM, ctx->stream);
+            if (p->pull) { gt::pull_x_arrived(p); gt::pull_state_out(p); }   // hot-order working state -> V (one pass per execute, inside the timed window)
+            GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
+            if (peer_used) GT_CUDA(cudaMemcpyAsync(&p->h_active[2], gt::peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, ctx->stream));
+            GT_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (peer_used && (uint32_t) p->h_active[2]) {
+                const uint32_t who = (uint32_t) p->h_active[2] - 1;
+                p->h_active[2] = 0;
+                p->poisoned = true;
+                cudaMemsetAsync(gt::peer_error_word(ctx), 0, 4, ctx->stream);
+                throw gt::Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " + std::to_string(who) +
+                                                 " (results are invalid; free this program and create a new one)");
             }
         }
-        if (p->pull) { gt::pull_x_arrived(p); gt::pull_state_out(p); }   // hot-order working state -> V (one pass per execute, inside the timed window)
-        GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
-        const bool peer_used = p->wx || p->wy || p->wxn;
-        if (peer_used) GT_CUDA(cudaMemcpyAsync(&p->h_active[1], gt::peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, ctx->stream));
-        GT_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (peer_used && (uint32_t) p->h_active[1])
-            throw gt::Error(GT_ERR_NCCL, "gt_program_execute: NVLink peer exchange timed out waiting for group member " +
-                                             std::to_string((uint32_t) p->h_active[1] - 1) + " (results are invalid)");
         float ms = 0;
         GT_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         p->tm.execute_ms = ms;
@@ -1015,9 +710,11 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
 
 extern "C" int gt_program_run_phase(gt_program* p, int phase) {
     return gt::guarded([&] {
-        GT_REQUIRE(p && p->initialized, "gt_program_run_phase: program not initialized");
+        GT_REQUIRE(p, "gt_program_run_phase: NULL program");
         GT_REQUIRE(phase >= 0 && phase <= 2, "gt_program_run_phase: phase must be 0, 1 or 2");
         GT_CUDA(cudaSetDevice(p->ctx->device));
+        if (!p->initialized) gt::prog_initialize(p);
+        if (!p->stationary) { gt::ns_run_phase(p, phase); return; }
         if (p->pull) gt::pull_state_in(p);
         if (phase == 0) {
             p->x_ready = false;

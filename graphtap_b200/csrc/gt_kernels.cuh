@@ -69,18 +69,21 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
 constexpr int kPushThreads = 256;
 constexpr int kPushPerThread = GT_PUSH_CHUNK / kPushThreads;   // 8 edges = two 128-bit loads
 
-template <int S, bool WEIGHTED, bool SKIP_INF>
-__global__ void __launch_bounds__(kPushThreads)
-k_spmv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
-            const uint32_t* __restrict__ chunk_col, uint32_t nchunks, uint64_t nnz,
-            const typename Semiring<S>::T* __restrict__ x, typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t) {
+// IMPROVED (engine, min semirings): t marks the rows whose y really decreased — what a follower owes its leader —
+// instead of every visited row (the kernel-level entry point keeps the reference's meaning, :1486).
+template <int S, bool WEIGHTED, bool SKIP_INF, bool IMPROVED>
+__device__ __forceinline__ void
+spmv_push_chunks(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
+                 const uint32_t* __restrict__ chunk_col, uint32_t nchunks, uint64_t nnz,
+                 const typename Semiring<S>::T* __restrict__ x, typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t,
+                 uint32_t first_chunk, uint32_t chunk_stride) {
     typedef Semiring<S> SR;
     typedef typename SR::T T;
     __shared__ uint32_t colof[GT_PUSH_CHUNK];
     __shared__ uint32_t warp_max[kPushThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    for (uint32_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    for (uint32_t chunk = first_chunk; chunk < nchunks; chunk += chunk_stride) {
         const uint64_t e0 = (uint64_t) chunk * GT_PUSH_CHUNK;
         const uint32_t cnt = (uint32_t) min((uint64_t) GT_PUSH_CHUNK, nnz - e0);
         const uint32_t c0 = chunk_col[chunk];
@@ -144,12 +147,26 @@ k_spmv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, co
                 if (k >= m) break;
                 if (cols[k] != last) { xv = __ldg(x + cols[k]); last = cols[k]; }
                 if (SKIP_INF && SR::skip(xv)) continue;
-                SR::reduce_dense(y + rows[k], WEIGHTED ? SR::mul(xv, wts[k]) : xv);
-                if (t) t[rows[k]] = 1;
+                const T val = WEIGHTED ? SR::mul(xv, wts[k]) : xv;
+                if constexpr (IMPROVED) {
+                    if (t) { if (val < __ldcg(y + rows[k]) && val < atomicMin(y + rows[k], val)) t[rows[k]] = 1; }
+                    else SR::reduce_dense(y + rows[k], val);
+                } else {
+                    SR::reduce_dense(y + rows[k], val);
+                    if (t) t[rows[k]] = 1;
+                }
             }
         }
         __syncthreads();                                // colof is rewritten by the next chunk
     }
+}
+
+template <int S, bool WEIGHTED, bool SKIP_INF>
+__global__ void __launch_bounds__(kPushThreads)
+k_spmv_push(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
+            const uint32_t* __restrict__ chunk_col, uint32_t nchunks, uint64_t nnz,
+            const typename Semiring<S>::T* __restrict__ x, typename Semiring<S>::T* __restrict__ y, uint8_t* __restrict__ t) {
+    spmv_push_chunks<S, WEIGHTED, SKIP_INF, false>(JA, IA, A, chunk_col, nchunks, nnz, x, y, t, blockIdx.x, gridDim.x);
 }
 
 // ---- pull SpMV (_COL_ ordering): y[j] (+)= sum over column j of x[IA[i]] ---------------------------------

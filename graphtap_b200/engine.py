@@ -266,6 +266,10 @@ class Vertex_Program:
         Env.print_time("Execute", self.timing().execute_ms * 1e-3)
         return self.iteration
 
+    def run_phase(self, phase: int):
+        """One phase of one iteration in isolation (0 scatter_gather, 1 combine, 2 apply); `iteration` does not advance."""
+        check(lib().gt_program_run_phase(self._ensure(), int(phase)))
+
     def timing(self) -> capi.Timing:
         t = capi.Timing()
         check(lib().gt_program_timing(self._ensure(), C.byref(t)))

@@ -406,3 +406,70 @@ def test_vertex_classification_matches_reference(fixture_unweighted):
     assert (reg.value, src.value, snk.value) == (550, 316, 21)
     assert G.rowgrp_maps(0)[2] == 866 and G.colgrp_maps(0)[2] == 571
     G.free()
+
+
+def test_sssp_on_the_unweighted_build(rmat12):
+    """Without -DHAS_WEIGHT the reference's SSSP combiner takes min(y, x) and the applicator adds 1
+    (src/apps/sssp.h:53-56,60-64): hop counts over the directed graph."""
+    E, O = _E(), _O()
+    tri = rmat12[:, :2].copy()
+    fl = dict(O.APP_FLAGS["sssp"]); fl.pop("weighted")
+    og = O.OracleGraph(tri, 4096, 1, weighted=0, **fl)
+    ref, rit, _ = og.nonstationary(O.SSSP, 0)
+    og.close()
+    G = E.Graph(weighted=False)
+    G.load_triples(tri, 4096, compression_type=E._TCSC_, **{k: bool(v) for k, v in fl.items()})
+    V = E.SSSP_Program(G, False, True, False, E._ROW_)
+    V.root = 0
+    assert V.execute() == rit
+    assert (V.V["distance"][:4097] == ref[:4097]).all()
+    V.free(); G.free()
+
+
+def test_execute_in_pieces_and_phase_by_phase(rmat12):
+    """execute(k) continues where the last call stopped (iteration counts are absolute, vertex_program.hpp:407-433), and
+    the three phases driven one by one give the same states as execute()."""
+    E, O = _E(), _O()
+    ref, rit = O.run_app("sssp", rmat12, 4096, 1, 0)
+    G = E.Graph(weighted=True)
+    G.load_triples(rmat12, 4096, directed=True, transpose=True, self_loops=False, parallel_edges=False, compression_type=E._TCSC_)
+    V = E.SSSP_Program(G, False, True, False, E._ROW_)
+    V.execute(2); V.execute(4)
+    assert V.execute() == rit
+    assert (V.V["distance"][:4097] == ref[:4097]).all()
+    V.free(); G.free()
+    tu = rmat12[:, :2].copy()
+    G = E.Graph(weighted=False)
+    G.load_triples(tu, 4096, directed=False, transpose=False, self_loops=True, parallel_edges=False, compression_type=E._TCSC_)
+    A = E.CC_Program(G, False, True, False, E._ROW_); A.execute(3)
+    B = E.CC_Program(G, False, True, False, E._ROW_)
+    for _ in range(3):
+        for ph in (0, 1, 2):
+            B.run_phase(ph)
+    assert (A.V["label"] == B.V["label"]).all()
+    refc, _ = O.run_app("cc", tu, 4096, 1, None)
+    B.execute()
+    assert (B.V["label"][:4097] == refc[:4097]).all()
+    A.free(); B.free(); G.free()
+
+
+@pytest.mark.parametrize("scale,seed", [(12, 12), (17, 4)])
+def test_bfs_bottom_up_equals_top_down(scale, seed):
+    """The bottom-up pass (one GPU, undirected graph) must leave exactly the parents and hops of the reference's push:
+    the first active neighbour in ascending order is the minimum the min-combiner would keep (src/apps/bfs.h:61-63)."""
+    from graphtap_b200.rmat import rmat_edges
+    E, O = _E(), _O()
+    tri = rmat_edges(scale, seed=seed)
+    n = 1 << scale
+    ref, rit = O.run_app("bfs", tri, n, 1, 0)
+    G = E.Graph(weighted=False)
+    G.load_triples(tri, n, directed=False, transpose=False, self_loops=False, parallel_edges=False, compression_type=E._TCSC_)
+    for ratio in (0.0, 0.05, 1e-9):                 # never / default / from the second iteration on
+        V = E.BFS_Program(G, False, False, True, E._ROW_)
+        V.set("bfs_bottom_up_ratio", ratio)
+        assert V.execute() == rit
+        mine = V.V
+        for f in ("parent", "hops"):
+            assert (mine[f][: n + 1] == ref[f][: n + 1]).all(), (ratio, f)
+        V.free()
+    G.free()

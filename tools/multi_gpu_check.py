@@ -64,6 +64,47 @@ def main():
                 V.free(); G.free()
                 print(f"[rank {rank}/{p}] {name} {app}{'' if layout is None else ' layout ' + str(layout)}: iters {V.iteration}/{rit} {detail} checksum {cs} -> {'OK' if good else 'FAIL'}", flush=True)
                 ok &= good
+    # ---- windows across calls: execute() twice on one program, and the three phases driven one by one ----
+    tw = rmat_edges(13, seed=14, weighted=True)
+    n = 1 << 13
+
+    def load_w(G, **fl):
+        ct = fl.pop("compression_type")
+        G.load_triples(tw, n, compression_type=ct, **fl)
+
+    def load_u(G, **fl):
+        ct = fl.pop("compression_type")
+        G.load_triples(tw[:, :2].copy(), n, compression_type=ct, **fl)
+
+    ref, rit = O.run_app("sssp", tw, n, p, 0)
+    G = E.Graph(weighted=True)
+    load_w(G, directed=True, transpose=True, self_loops=False, acyclic=False, parallel_edges=False, compression_type=E._TCSC_)
+    V = E.SSSP_Program(G, False, True, False, E._ROW_)
+    V.root = 0
+    V.execute(2)                      # two fixed iterations ...
+    V.execute(4)                      # ... two more (iteration counts are absolute, as in the reference) ...
+    it = V.execute()                  # ... then until convergence, all on the same windows
+    lay = G.info().layout
+    mine = V.V["distance"]
+    good = it == rit and bool((mine == ref[lay.owned_segment * lay.tile_height:(lay.owned_segment + 1) * lay.tile_height]).all())
+    print(f"[rank {rank}/{p}] sssp execute(2)+execute(4)+execute(): iters {it}/{rit} -> {'OK' if good else 'FAIL'}", flush=True)
+    ok &= good
+    V.free(); G.free()
+    G = E.Graph(weighted=False)
+    load_u(G, directed=False, transpose=False, self_loops=True, acyclic=False, parallel_edges=False, compression_type=E._TCSC_)
+    A = E.CC_Program(G, False, True, False, E._ROW_)
+    A.execute(3)
+    B = E.CC_Program(G, False, True, False, E._ROW_)
+    for _ in range(3):                # CC's applicator does not depend on the iteration number: 3 rounds of phases == execute(3)
+        for ph in (0, 1, 2):
+            B.run_phase(ph)
+    good = bool((A.V["label"] == B.V["label"]).all())
+    B.execute()                       # and the program is still usable afterwards
+    refc, _ = O.run_app("cc", tw[:, :2].copy(), n, p, None)
+    good &= bool((B.V["label"] == refc[lay.owned_segment * lay.tile_height:(lay.owned_segment + 1) * lay.tile_height]).all())
+    print(f"[rank {rank}/{p}] cc run_phase x3 == execute(3), then execute(): {'OK' if good else 'FAIL'}", flush=True)
+    ok &= good
+    A.free(); B.free(); G.free()
     E.Env.barrier()
     print(f"[rank {rank}] MULTI_GPU_CHECK {'PASS' if ok else 'FAIL'}", flush=True)
     E.Env.finalize()
