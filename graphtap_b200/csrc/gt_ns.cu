@@ -47,6 +47,11 @@ struct NsTile {                                  // one local tile (device array
     uint32_t* y; uint8_t* t;                     // running-min y of its row segment; improved-row flags (segments led by another rank) or nullptr
     uint64_t dense_bytes;                        // algorithmic bytes of one dense pass
 };
+// The tile passes take their descriptors BY VALUE, eight at a time: kernel parameters live in the constant bank and cost
+// no registers (the first version loaded them from a device array and lost two CTAs per SM of occupancy to the
+// pointers it kept live).
+constexpr int kNsGroup = 8;
+struct NsTiles { NsTile t[kNsGroup]; };
 struct NsYSend {                                 // a row segment led by another rank: its partial y goes to the leader
     uint32_t* y; uint8_t* t; uint32_t n;
     uint32_t* yi; uint32_t* yv; unsigned int* count;     // local staging list of the improved rows
@@ -68,7 +73,8 @@ struct NsState {
     std::vector<uint32_t*> y;
     DevBuf<uint8_t> T;                           // improved flags, R x ychunk (used for the slots this rank does not lead)
     DevBuf<uint32_t> ystage;                     // (yi, yv) staging, 2 x ychunk per send slot
-    DevBuf<NsTile> tiles; int ntiles = 0;
+    DevBuf<NsTile> tiles; int ntiles = 0;        // device copy (the heavy-column kernel indexes it by list entry)
+    std::vector<NsTile> htiles;                  // host copy, handed to the tile passes by value
     DevBuf<NsYSend> ysend; DevBuf<NsYRecv> yrecv; int nsend = 0, nrecv = 0;
     DevBuf<uint2> heavy_list;
     DevBuf<unsigned int> slot_counts;            // NCCL exchange only: frontier size of every x slot
@@ -171,19 +177,27 @@ __global__ void k_ns_header(const unsigned int* __restrict__ count, uint32_t n, 
 }
 
 // ---- combine: the tile passes ----------------------------------------------------------------------------------------------
+// `filter`: read y first and skip the RED when it cannot win (y only ever decreases, so a stale read is safe).  Pays
+// when the frontier is large — RMAT's hub rows settle after a few updates and stop serialising in L2 — and costs an
+// extra L2 round trip when most updates are first visits, so the caller switches it on by frontier size.
 template <int S>
-__device__ __forceinline__ void ns_reduce(typename Semiring<S>::T* y, uint8_t* t, uint32_t r, typename Semiring<S>::T v) {
+__device__ __forceinline__ void ns_reduce(typename Semiring<S>::T* y, uint8_t* t, uint32_t r, typename Semiring<S>::T v, bool filter) {
+    if (filter && v >= __ldcg(y + r)) return;
     if (t) { if (v < atomicMin(y + r, v)) t[r] = 1; }      // the row improved in this iteration: it goes to the leader
     else Semiring<S>::reduce(y + r, v);
 }
 
-// frontier SpMSpV over every local tile whose column segment travelled as a list (:1476-1488)
+// frontier SpMSpV over every local tile whose column segment travelled as a list (:1476-1488).
+// A CTA takes a batch of B frontier columns, block-scans their lengths and spreads the batch's EDGES over its 256
+// threads.  B follows the frontier: with few columns (the first iterations out of a hub) every CTA gets one or a few of
+// them, so no CTA is left walking hundreds of long columns alone; with millions, B = 256.
 template <int S, bool WEIGHTED>
-__global__ void __launch_bounds__(kNsBatch)
-k_ns_spmspv(const NsTile* __restrict__ tiles, uint2* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kNsBatch, 6)
+k_ns_spmspv(const __grid_constant__ NsTiles tiles, int tile0, uint2* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count,
+            unsigned long long* __restrict__ stats) {
     typedef Semiring<S> SR;
     typedef typename SR::T T;
-    const NsTile Q = tiles[blockIdx.y];
+    const NsTile& Q = tiles.t[blockIdx.y];
     if (!Q.nnz || Q.hdr[0] != NS_SPARSE) return;
     const uint32_t k = Q.hdr[1];
     if (blockIdx.x == 0 && threadIdx.x == 0 && k) stats[2] = 1;
@@ -192,12 +206,15 @@ k_ns_spmspv(const NsTile* __restrict__ tiles, uint2* __restrict__ heavy_list, un
     __shared__ uint32_t s_start[kNsBatch], s_off[kNsBatch];
     __shared__ T s_val[kNsBatch];
     const uint32_t tid = threadIdx.x;
+    const bool filter = k > (Q.ncols >> 5);                           // more than 3 % of the columns active
+    uint32_t B = (k + gridDim.x - 1) / gridDim.x;                     // columns per batch: 1 .. 256
+    B = B < 1 ? 1 : B > (uint32_t) kNsBatch ? (uint32_t) kNsBatch : B;
     unsigned long long bytes = 0;
-    for (uint32_t base = blockIdx.x * kNsBatch; base < k; base += gridDim.x * kNsBatch) {
+    for (uint32_t base = blockIdx.x * B; base < k; base += gridDim.x * B) {
         const uint32_t f = base + tid;
         uint32_t len = 0, b = 0;
         T v = SR::identity();
-        if (f < k) {
+        if (tid < B && f < k) {
             const uint32_t j = Q.xi[f];
             v = Q.xv[f];
             b = Q.JA[j];
@@ -206,7 +223,7 @@ k_ns_spmspv(const NsTile* __restrict__ tiles, uint2* __restrict__ heavy_list, un
             if (len > kNsHeavyColumn) {
                 const uint32_t nch = (len + kNsHeavyChunk - 1) / kNsHeavyChunk;
                 const unsigned hb = atomicAdd(heavy_count, nch);
-                for (uint32_t c = 0; c < nch; c++) heavy_list[hb + c] = make_uint2(f, (blockIdx.y << 24) | c);
+                for (uint32_t c = 0; c < nch; c++) heavy_list[hb + c] = make_uint2(f, ((uint32_t) (tile0 + blockIdx.y) << 24) | c);
                 len = 0;
             }
         }
@@ -215,7 +232,7 @@ k_ns_spmspv(const NsTile* __restrict__ tiles, uint2* __restrict__ heavy_list, un
         s_start[tid] = b; s_val[tid] = v; s_off[tid] = off;
         __syncthreads();
         for (uint32_t idx = tid; idx < total; idx += kNsBatch) {
-            uint32_t lo = 0, hi = kNsBatch;                          // first c with s_off[c] > idx; the column is the one before
+            uint32_t lo = 0, hi = B;                                 // first c with s_off[c] > idx; the column is the one before
             while (lo < hi) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (s_off[mid] <= idx) lo = mid + 1; else hi = mid;
@@ -223,7 +240,7 @@ k_ns_spmspv(const NsTile* __restrict__ tiles, uint2* __restrict__ heavy_list, un
             const uint32_t c = lo - 1;
             const uint32_t i = s_start[c] + (idx - s_off[c]);
             const uint32_t r = ld_stream_u32(Q.IA + i);
-            ns_reduce<S>(Q.y, Q.t, r, WEIGHTED ? SR::mul(s_val[c], ld_stream_u32(Q.A + i)) : s_val[c]);
+            ns_reduce<S>(Q.y, Q.t, r, WEIGHTED ? SR::mul(s_val[c], ld_stream_u32(Q.A + i)) : s_val[c], filter);
         }
         __syncthreads();
     }
@@ -244,18 +261,19 @@ k_ns_heavy(const NsTile* __restrict__ tiles, const uint2* __restrict__ heavy_lis
         const uint32_t j = Q.xi[fc.x];
         const T v = Q.xv[fc.x];
         const uint32_t b = Q.JA[j] + (fc.y & 0xffffffu) * kNsHeavyChunk, e = min(Q.JA[j + 1], b + kNsHeavyChunk);
+        const bool filter = Q.hdr[1] > (Q.ncols >> 5);
         for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
             const uint32_t r = ld_stream_u32(Q.IA + i);
-            ns_reduce<S>(Q.y, Q.t, r, WEIGHTED ? SR::mul(v, ld_stream_u32(Q.A + i)) : v);
+            ns_reduce<S>(Q.y, Q.t, r, WEIGHTED ? SR::mul(v, ld_stream_u32(Q.A + i)) : v, filter);
         }
     }
 }
 
 // dense SpMV skipping infinity() over every local tile whose column segment travelled dense (:1491-1502)
 template <int S, bool WEIGHTED>
-__global__ void __launch_bounds__(kPushThreads)
-k_ns_dense(const NsTile* __restrict__ tiles, unsigned long long* __restrict__ stats) {
-    const NsTile Q = tiles[blockIdx.y];
+__global__ void __launch_bounds__(kPushThreads, 8)
+k_ns_dense(const __grid_constant__ NsTiles tiles, unsigned long long* __restrict__ stats) {
+    const NsTile& Q = tiles.t[blockIdx.y];
     if (!Q.nnz || Q.hdr[0] != NS_DENSE) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats, (unsigned long long) Q.dense_bytes);
     spmv_push_chunks<S, WEIGHTED, true, true>(Q.JA, Q.IA, Q.A, Q.chunk_col, Q.nchunks, Q.nnz, (const typename Semiring<S>::T*) Q.x,
@@ -267,8 +285,8 @@ k_ns_dense(const NsTile* __restrict__ tiles, unsigned long long* __restrict__ st
 // still infinity() (any earlier active neighbour would have visited it), so the first active neighbour found is the
 // minimum the reference's push would have left there (src/apps/bfs.h:61-63).
 __global__ void __launch_bounds__(256)
-k_ns_bfs_bottom_up(const NsTile* __restrict__ tiles, const uint32_t* __restrict__ JC, const uint32_t* __restrict__ hops, unsigned long long* __restrict__ stats) {
-    const NsTile Q = tiles[0];
+k_ns_bfs_bottom_up(const __grid_constant__ NsTiles tiles, const uint32_t* __restrict__ JC, const uint32_t* __restrict__ hops, unsigned long long* __restrict__ stats) {
+    const NsTile& Q = tiles.t[0];
     if (Q.hdr[0] != NS_BOTTOM_UP) return;
     unsigned long long bytes = 0;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < Q.ncols; j += gridDim.x * blockDim.x) {
@@ -486,6 +504,7 @@ void ns_alloc(gt_program* P) {
     }
     N.tiles.alloc(N.ntiles);
     GT_CUDA(cudaMemcpyAsync(N.tiles.p, ht.data(), ht.size() * sizeof(NsTile), cudaMemcpyHostToDevice, st));
+    N.htiles = ht;
     N.heavy_list.alloc(nnz_all / kNsHeavyChunk + nnz_all / kNsHeavyColumn + 64);
     N.nsend = N.nrecv = N.wy ? N.G - 1 : 0;
     N.counters.alloc(3 + 2 * (size_t) std::max(1, N.nsend));
@@ -626,21 +645,31 @@ static void ns_combine(gt_program* P) {
     cudaStream_t st = ctx->stream;
     const gt_graph* g = P->g;
     GT_CUDA(cudaMemsetAsync(N.counters.p, 0, 2 * sizeof(unsigned int), st));       // heavy count; the frontier count the applicator appends to
-    const int gx = std::max(1, ctx->sm_count * 8 / N.ntiles);                      // 8 CTAs of 256 threads per SM over all tiles
-    const dim3 gs(gx, N.ntiles), gd(gx, N.ntiles);
     const int hgrid = ctx->sm_count * 4;
+    const int nper = std::min(N.ntiles, kNsGroup);
+    const int gx = std::max(1, ctx->sm_count * 8 / nper);                          // 8 CTAs of 256 threads per SM over the tiles of a launch
+    auto group = [&](int t0) {
+        NsTiles Tg{};
+        for (int i = 0; i < kNsGroup && t0 + i < N.ntiles; i++) Tg.t[i] = N.htiles[t0 + i];
+        return Tg;
+    };
 #define GT_NS_PASS(S, W) do { \
-        k_ns_spmspv<S, W><<<gs, kNsBatch, 0, st>>>(N.tiles.p, N.heavy_list.p, N.counters.p, N.stats.p); \
+        for (int t0 = 0; t0 < N.ntiles; t0 += kNsGroup) { \
+            k_ns_spmspv<S, W><<<dim3(gx, std::min(kNsGroup, N.ntiles - t0)), kNsBatch, 0, st>>>(group(t0), t0, N.heavy_list.p, N.counters.p, N.stats.p); \
+            ctx->kernel_launches++; \
+        } \
         if (N.any_heavy) { k_ns_heavy<S, W><<<hgrid, 256, 0, st>>>(N.tiles.p, N.heavy_list.p, N.counters.p); ctx->kernel_launches++; } \
-        k_ns_dense<S, W><<<gd, kPushThreads, 0, st>>>(N.tiles.p, N.stats.p); \
-        ctx->kernel_launches += 2; \
+        for (int t0 = 0; t0 < N.ntiles; t0 += kNsGroup) { \
+            k_ns_dense<S, W><<<dim3(gx, std::min(kNsGroup, N.ntiles - t0)), kPushThreads, 0, st>>>(group(t0), N.stats.p); \
+            ctx->kernel_launches++; \
+        } \
     } while (0)
     if (P->semiring == GT_MIN_PLUS_U32) GT_NS_PASS(GT_MIN_PLUS_U32, true);
     else if (g->weighted) GT_NS_PASS(GT_MIN_SELECT_U32, true);
     else GT_NS_PASS(GT_MIN_SELECT_U32, false);
 #undef GT_NS_PASS
     if (N.bottom_up_ok && P->bfs_bottom_up_ratio > 0.0) {
-        k_ns_bfs_bottom_up<<<grid_for((*P->pcol)[0].nnz, 256, ctx->sm_count, 8), 256, 0, st>>>(N.tiles.p, (*P->pcol)[0].ids.p, P->b.p, N.stats.p);
+        k_ns_bfs_bottom_up<<<grid_for((*P->pcol)[0].nnz, 256, ctx->sm_count, 8), 256, 0, st>>>(group(0), (*P->pcol)[0].ids.p, P->b.p, N.stats.p);
         ctx->kernel_launches++;
     }
     if (N.wy) {

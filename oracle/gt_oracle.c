@@ -218,6 +218,106 @@ const uint8_t* gto_seg_bits(const gto_graph* g, int is_col, uint32_t s) { return
 const uint32_t* gto_seg_prefix(const gto_graph* g, int is_col, uint32_t s) { return (is_col ? g->cols : g->rows)[s].prefix; }
 const uint32_t* gto_seg_ids(const gto_graph* g, int is_col, uint32_t s) { return (is_col ? g->cols : g->rows)[s].ids; }
 
+/* ---- TCSC_CF: classify_vertices (src/mat/matrix.hpp:1124-1144) + TCSC_CF_BASE::populate (src/ds/compressed_column.hpp:671-1114)
+ * Restated literally, quirks included: the swap runs only if the column holds a non-source entry
+ * (:682), NC_SRC_R_SNK_C counts EDGES (:1046-1049) and its ranges start at JA[j] + n (:1094).  One call produces, for
+ * tile (rg, cg): the CF-ordered IA (and A), and the four (start,end)-pair lists with their JC lists.
+ * kind: 0 REG_R_REG_C, 1 REG_R_SNK_C, 2 SRC_R_REG_C, 3 SRC_R_SNK_C. */
+typedef struct {
+    uint32_t* IA; uint32_t* A;
+    uint32_t NC[4];            /* allocated pairs (the reference's NC_*) */
+    uint32_t filled[4];        /* pairs actually written (== NC except for SRC_R_SNK_C) */
+    uint32_t* JA[4];           /* 2 * NC */
+    uint32_t* JC[4];           /* NC */
+} gto_cf_tile;
+
+/* vertex classes of segment s: 1 regular (row and column non-empty), 2 source row (row only), 3 sink column (column only), 0 neither */
+void gto_classify(const gto_graph* g, uint32_t s, uint8_t* cls) {
+    for (uint32_t i = 0; i < g->th; i++) {
+        const int r = g->rows[s].bits[i], c = g->cols[s].bits[i];
+        cls[i] = (uint8_t) (r && c ? 1 : r ? 2 : c ? 3 : 0);                       /* matrix.hpp:1135-1144 */
+    }
+}
+
+void gto_cf_free(gto_cf_tile* T) {
+    if (!T) return;
+    free(T->IA); free(T->A);
+    for (int k = 0; k < 4; k++) { free(T->JA[k]); free(T->JC[k]); }
+    free(T);
+}
+
+gto_cf_tile* gto_cf_build(const gto_graph* g, uint32_t rg, uint32_t cg) {
+    const tile_t* B = &g->tiles[rg * g->p + cg];
+    const uint32_t nnzcols = g->cols[cg].nnz;
+    const uint32_t* JA = B->JA;
+    const uint32_t* JC = g->cols[cg].ids;
+    const uint32_t* IR = g->rows[rg].ids;
+    gto_cf_tile* T = (gto_cf_tile*) calloc(1, sizeof(gto_cf_tile));
+    const uint64_t m = B->nnz;
+    T->IA = (uint32_t*) malloc(4 * (m ? m : 1)); T->A = (uint32_t*) malloc(4 * (m ? m : 1));
+    memcpy(T->IA, B->IA, 4 * m); memcpy(T->A, B->A, 4 * m);
+    uint32_t* IA = T->IA; uint32_t* A = T->A;
+    uint8_t* rcls = (uint8_t*) malloc(g->th); uint8_t* ccls = (uint8_t*) malloc(g->th);
+    gto_classify(g, rg, rcls); gto_classify(g, cg, ccls);
+#define SRC(i) (rcls[IR[IA[i]]] == 2)                                             /* source_rows_bitvector[IR[IA[i]]] */
+    /* "Moving source rows to the end" :671-708 */
+    uint32_t* r = (uint32_t*) malloc(4 * (m ? m : 1));
+    for (uint32_t j = 0; j < nnzcols; j++) {
+        uint32_t n = 0, mm = 0;
+        for (uint32_t i = JA[j]; i < JA[j + 1]; i++) if (SRC(i)) { mm = JA[j + 1] - JA[j]; r[n++] = i; }
+        if (mm > 0 && mm > n) {
+            for (uint32_t pp = 0; pp < n; pp++) {
+                for (uint32_t q = JA[j + 1] - 1; ; q--) {                         /* the reference's q >= JA[j] cannot fail: mm > n */
+                    if (!SRC(q)) { uint32_t t = IA[r[pp]]; IA[r[pp]] = IA[q]; IA[q] = t; t = A[r[pp]]; A[r[pp]] = A[q]; A[q] = t; break; }
+                    else if (r[pp] == q) break;
+                }
+            }
+        }
+    }
+    free(r);
+    /* the four lists; a column is "local" when it has entries in this tile (:649-657) */
+    for (int kind = 0; kind < 4; kind++) {
+        const int want_col = (kind == 0 || kind == 2) ? 1 : 3;                     /* regular / sink columns of the column group */
+        for (int pass = 0; pass < 2; pass++) {
+            uint32_t l = 0, o = 0, kcnt = 0;
+            for (uint32_t j = 0; j < nnzcols; j++) {
+                if (JA[j] == JA[j + 1] || ccls[JC[j]] != want_col) continue;      /* the JC_LOCAL_VAL x {regular,sink}_columns merge */
+                uint32_t n = 0;
+                const uint32_t len = JA[j + 1] - JA[j];
+                for (uint32_t i = JA[j]; i < JA[j + 1]; i++) if (SRC(i)) n++;
+                if (kind <= 1) {                                                  /* :749-833, :862-946: regular rows */
+                    if (n == len) continue;                                       /* all-source column: no pair */
+                    if (pass) { T->JA[kind][2 * l] = JA[j]; T->JA[kind][2 * l + 1] = JA[j + 1] - n; T->JC[kind][o++] = j; }
+                    l++;
+                } else if (kind == 2) {                                           /* :949-1022 */
+                    if (!n) continue;
+                    if (pass) { T->JA[kind][2 * l] = JA[j + 1] - n; T->JA[kind][2 * l + 1] = JA[j + 1]; T->JC[kind][o++] = j; }
+                    l++;
+                } else {                                                          /* :1025-1108: NC counts edges, start is JA[j] + n */
+                    kcnt += n;
+                    if (!n) continue;
+                    if (pass) { T->JA[kind][2 * l] = JA[j] + n; T->JA[kind][2 * l + 1] = JA[j + 1]; T->JC[kind][o++] = j; }
+                    l++;
+                }
+            }
+            if (!pass) {
+                T->NC[kind] = kind == 3 ? kcnt : l;
+                T->JA[kind] = (uint32_t*) calloc(2 * (size_t) T->NC[kind] + 1, 4);
+                T->JC[kind] = (uint32_t*) calloc((size_t) T->NC[kind] + 1, 4);
+            } else T->filled[kind] = l;
+        }
+    }
+#undef SRC
+    free(rcls); free(ccls);
+    return T;
+}
+uint32_t gto_cf_nc(const gto_cf_tile* T, int kind) { return T->NC[kind]; }
+uint32_t gto_cf_filled(const gto_cf_tile* T, int kind) { return T->filled[kind]; }
+const uint32_t* gto_cf_ja(const gto_cf_tile* T, int kind) { return T->JA[kind]; }
+const uint32_t* gto_cf_jc(const gto_cf_tile* T, int kind) { return T->JC[kind]; }
+const uint32_t* gto_cf_ia(const gto_cf_tile* T) { return T->IA; }
+const uint32_t* gto_cf_a(const gto_cf_tile* T) { return T->A; }
+
 /* ---- one tile, one semiring: spmv_stationary / spmv_nonstationary ------------------------------------
  * semiring 0 plus-times f64 (pr.h:35-41), 1 min-plus u32 (sssp.h:49-52), 2 min-select u32 (bfs.h:61-63)
  * ordering 0 = _ROW_ (vertex_program.hpp:1164-1172), 1 = _COL_ (:1175-1183) */
@@ -327,6 +427,95 @@ uint32_t gto_pagerank(const gto_graph* g, uint32_t iters, double alpha, double t
     if (deg_out) memcpy(deg_out, deg, sizeof(uint32_t) * nall);
     for (uint32_t s = 0; s < p; s++) free(X[s]);
     free(X); free(part); free(deg);
+    return it;
+}
+
+/* ---- PageRank on _TCSC_CF_ tiles: the computation-filtering schedule ----------------------------------------------------
+ * spmv_stationary's TCSC_CF branch (vertex_program.hpp:1218-1325): iteration 0 adds REG_R x SNK_C, every (non-converged)
+ * iteration REG_R x REG_C, the last iteration (fixed count) SRC_R x REG_C and SRC_R x SNK_C — the latter guarded by
+ * NC_SRC_R_REG_C (:1302) and walking NC_SRC_R_SNK_C pairs.  apply_stationary's CF branch (:1671-1692): regular rows every
+ * iteration, source rows only on the last.  has_converged over the regular rows only (:1902-1916).  In convergence mode
+ * combine() does NOTHING after convergence for _TCSC_CF_ (:1036-1043), so the final apply() gives every source row
+ * alpha + (1 - alpha) * 0: the "quirky path" of SURVEY.md §8c (fixture: 12 iterations, checksum 51). */
+uint32_t gto_pagerank_cf(const gto_graph* g, uint32_t iters, double alpha, double tol, double* rank, uint32_t* deg_out) {
+    const uint32_t p = g->p, th = g->th;
+    const size_t nall = (size_t) p * th;
+    uint32_t* deg = (uint32_t*) malloc(sizeof(uint32_t) * nall);
+    gto_degree(g, 1, deg);
+    for (uint32_t s = 0; s < p; s++)
+        for (uint32_t i = 0; i < th; i++)
+            if (!g->rows[s].bits[i]) deg[(size_t) s * th + i] = 0;
+    for (size_t v = 0; v < nall; v++) rank[v] = alpha;
+    gto_cf_tile** CF = (gto_cf_tile**) calloc((size_t) p * p, sizeof(gto_cf_tile*));
+    for (uint32_t t = 0; t < p * p; t++) if (g->tiles[t].nnz) CF[t] = gto_cf_build(g, t / p, t % p);
+    uint8_t** cls = (uint8_t**) malloc(sizeof(uint8_t*) * p);
+    for (uint32_t s = 0; s < p; s++) { cls[s] = (uint8_t*) malloc(th); gto_classify(g, s, cls[s]); }
+    double** X = (double**) malloc(sizeof(double*) * p);
+    for (uint32_t s = 0; s < p; s++) X[s] = (double*) malloc(sizeof(double) * (g->cols[s].nnz ? g->cols[s].nnz : 1));
+    double** part = (double**) malloc(sizeof(double*) * p);
+    double** Ylead = (double**) calloc(p, sizeof(double*));          /* the leader's y of every row group, kept for the final apply() */
+    uint32_t it = 0;
+    int converged = 0;
+    const int check = iters == 0;
+    for (;;) {
+        for (uint32_t s = 0; s < p; s++)
+            for (uint32_t j = 0; j < g->cols[s].nnz; j++) {
+                const size_t v = (size_t) s * th + g->cols[s].ids[j];
+                X[s][j] = deg[v] ? rank[v] / deg[v] : 0.0;
+            }
+        const int last = !check && it + 1 == iters;
+        uint64_t moving = 0, nreg = 0;
+        for (uint32_t rg = 0; rg < p; rg++) {
+            const uint32_t nr = g->rows[rg].nnz;
+            for (uint32_t r = 0; r < p; r++) part[r] = NULL;
+            for (uint32_t cg = 0; cg < p; cg++) {
+                const int32_t owner = g->tile_rank[rg * p + cg];
+                if (!part[owner]) part[owner] = (double*) calloc(nr ? nr : 1, sizeof(double));
+                const gto_cf_tile* T = CF[rg * p + cg];
+                if (!T) continue;
+                double* y = part[owner];
+                const double* x = X[cg];
+#define GTO_CF_RUN(kind, count) for (uint32_t j = 0; j < (count); j++) { const uint32_t l = T->JC[kind][j]; \
+                    for (uint32_t i = T->JA[kind][2 * j]; i < T->JA[kind][2 * j + 1]; i++) y[T->IA[i]] += x[l]; }
+                if (it == 0) GTO_CF_RUN(1, T->NC[1])                              /* :1246-1262 */
+                GTO_CF_RUN(0, T->NC[0])                                           /* :1264-1281 */
+                if (last) {                                                       /* :1282-1317 */
+                    GTO_CF_RUN(2, T->NC[2])
+                    if (T->NC[2]) GTO_CF_RUN(3, T->NC[3])
+                }
+#undef GTO_CF_RUN
+            }
+            double* y = part[g->leader[rg]];
+            for (uint32_t r = 0; r < p; r++)
+                if (part[r] && (int32_t) r != g->leader[rg]) { for (uint32_t k = 0; k < nr; k++) y[k] += part[r][k]; }
+            for (uint32_t k = 0; k < nr; k++) {                        /* apply_stationary, CF branch :1671-1692 */
+                const uint32_t i = g->rows[rg].ids[k];
+                const size_t v = (size_t) rg * th + i;
+                const int c = cls[rg][i];
+                if (c == 1 || (c == 2 && last)) {
+                    const double tmp = rank[v];
+                    rank[v] = alpha + (1.0 - alpha) * y[k];
+                    if (c == 1) { nreg++; if (fabs(rank[v] - tmp) > tol) moving++; }
+                }
+            }
+            free(Ylead[rg]); Ylead[rg] = y;
+            for (uint32_t r = 0; r < p; r++) if ((int32_t) r != g->leader[rg]) free(part[r]);
+        }
+        it++;
+        if (check) {
+            if (moving == 0) { converged = 1; break; }                 /* :1902-1921 */
+        } else if (it >= iters) break;
+    }
+    if (converged)                                                     /* execute(): combine() (a no-op here) + apply() :425-429 */
+        for (uint32_t rg = 0; rg < p; rg++)
+            for (uint32_t k = 0; k < g->rows[rg].nnz; k++) {
+                const uint32_t i = g->rows[rg].ids[k];
+                if (cls[rg][i] == 2) rank[(size_t) rg * th + i] = alpha + (1.0 - alpha) * Ylead[rg][k];   /* y of a source row is still 0 */
+            }
+    if (deg_out) memcpy(deg_out, deg, sizeof(uint32_t) * nall);
+    for (uint32_t s = 0; s < p; s++) { free(X[s]); free(cls[s]); free(Ylead[s]); }
+    for (uint32_t t = 0; t < p * p; t++) gto_cf_free(CF[t]);
+    free(X); free(part); free(deg); free(CF); free(cls); free(Ylead);
     return it;
 }
 

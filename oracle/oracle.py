@@ -61,6 +61,16 @@ def lib() -> C.CDLL:
         l.gto_tile_spmspv_u32.argtypes = [vp, u32, u32, i32, vp, vp, u32, vp, vp]
         l.gto_degree.argtypes = [vp, i32, vp]
         l.gto_pagerank.restype = u32; l.gto_pagerank.argtypes = [vp, u32, C.c_double, C.c_double, vp, vp]
+        l.gto_pagerank_cf.restype = u32; l.gto_pagerank_cf.argtypes = [vp, u32, C.c_double, C.c_double, vp, vp]
+        l.gto_classify.argtypes = [vp, u32, vp]
+        l.gto_cf_build.restype = vp; l.gto_cf_build.argtypes = [vp, u32, u32]
+        l.gto_cf_free.argtypes = [vp]
+        for f in ("gto_cf_nc", "gto_cf_filled"):
+            getattr(l, f).restype = u32; getattr(l, f).argtypes = [vp, i32]
+        for f in ("gto_cf_ja", "gto_cf_jc"):
+            getattr(l, f).restype = vp; getattr(l, f).argtypes = [vp, i32]
+        for f in ("gto_cf_ia", "gto_cf_a"):
+            getattr(l, f).restype = vp; getattr(l, f).argtypes = [vp]
         l.gto_nonstationary.restype = u32; l.gto_nonstationary.argtypes = [vp, i32, u32, C.c_double, vp, vp, vp]
         l.gto_checksum_f64.argtypes = [vp, u64, vp, vp]
         l.gto_checksum_u32.argtypes = [vp, u64, u32, vp, vp]
@@ -137,10 +147,33 @@ class OracleGraph:
         lib().gto_degree(self.h, ordering, _ptr(d))
         return d
 
-    def pagerank(self, iters=20, alpha=0.15, tol=1e-5):
+    def classify(self, s: int) -> np.ndarray:
+        """classify_vertices of vertex segment s: 1 regular, 2 source row, 3 sink column, 0 neither (u8[tile_height])."""
+        out = np.zeros(self.th, dtype=np.uint8)
+        lib().gto_classify(self.h, s, _ptr(out))
+        return out
+
+    def cf_tile(self, rg: int, cg: int) -> dict:
+        """TCSC_CF_BASE::populate of tile (rg, cg): CF-ordered IA / A and the four pair lists
+        (kind 0 REG_R_REG_C, 1 REG_R_SNK_C, 2 SRC_R_REG_C, 3 SRC_R_SNK_C)."""
+        nnz = lib().gto_tile_nnz(self.h, rg, cg)
+        if not nnz:
+            return dict(nnz=0)
+        t = lib().gto_cf_build(self.h, rg, cg)
+        d = dict(nnz=nnz, IA=_view(lib().gto_cf_ia(t), nnz, "<u4"), A=_view(lib().gto_cf_a(t), nnz, "<u4"))
+        for k in range(4):
+            nc = lib().gto_cf_nc(t, k)
+            d[f"NC{k}"], d[f"filled{k}"] = nc, lib().gto_cf_filled(t, k)
+            d[f"JA{k}"] = _view(lib().gto_cf_ja(t, k), 2 * nc, "<u4")
+            d[f"JC{k}"] = _view(lib().gto_cf_jc(t, k), nc, "<u4")
+        lib().gto_cf_free(t)
+        return d
+
+    def pagerank(self, iters=20, alpha=0.15, tol=1e-5, cf=False):
+        """iters == 0: until convergence.  cf: the _TCSC_CF_ computation-filtering schedule (pr.cpp) instead of _TCSC_ (pr1.cpp)."""
         n = self.p * self.th
         V = np.zeros(n, dtype=PR_STATE); rank = np.zeros(n); deg = np.zeros(n, dtype=np.uint32)
-        it = lib().gto_pagerank(self.h, iters, alpha, tol, _ptr(rank), _ptr(deg))
+        it = (lib().gto_pagerank_cf if cf else lib().gto_pagerank)(self.h, iters, alpha, tol, _ptr(rank), _ptr(deg))
         V["rank"], V["degree"] = rank, deg
         return V, it
 

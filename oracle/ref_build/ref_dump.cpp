@@ -96,6 +96,17 @@ static void dump_tiles(G& graph) {
             write_raw(tb + ".IA.bin", c->IA, (size_t) c->nnz);
             write_raw(tb + ".JC.bin", c->JC, (size_t) c->nnzcols);
             write_raw(tb + ".IR.bin", c->IR, (size_t) c->nnzrows);
+            /* the four computation-filtering lists (src/ds/compressed_column.hpp:749-1114): NC pairs + NC column ids each */
+            std::ofstream cf(tb + ".cf.meta");
+            cf << c->NC_REG_R_REG_C << " " << c->NC_REG_R_SNK_C << " " << c->NC_SRC_R_REG_C << " " << c->NC_SRC_R_SNK_C << "\n";
+            write_raw(tb + ".cf0.JA.bin", c->JA_REG_R_REG_C, c->NC_REG_R_REG_C ? 2 * (size_t) c->NC_REG_R_REG_C : 0);
+            write_raw(tb + ".cf0.JC.bin", c->JC_REG_R_REG_C, c->NC_REG_R_REG_C ? (size_t) c->NC_REG_R_REG_C : 0);
+            write_raw(tb + ".cf1.JA.bin", c->JA_REG_R_SNK_C, c->NC_REG_R_SNK_C ? 2 * (size_t) c->NC_REG_R_SNK_C : 0);
+            write_raw(tb + ".cf1.JC.bin", c->JC_REG_R_SNK_C, c->NC_REG_R_SNK_C ? (size_t) c->NC_REG_R_SNK_C : 0);
+            write_raw(tb + ".cf2.JA.bin", c->JA_SRC_R_REG_C, c->NC_SRC_R_REG_C ? 2 * (size_t) c->NC_SRC_R_REG_C : 0);
+            write_raw(tb + ".cf2.JC.bin", c->JC_SRC_R_REG_C, c->NC_SRC_R_REG_C ? (size_t) c->NC_SRC_R_REG_C : 0);
+            write_raw(tb + ".cf3.JA.bin", c->JA_SRC_R_SNK_C, c->NC_SRC_R_SNK_C ? 2 * (size_t) c->NC_SRC_R_SNK_C : 0);
+            write_raw(tb + ".cf3.JC.bin", c->JC_SRC_R_SNK_C, c->NC_SRC_R_SNK_C ? (size_t) c->NC_SRC_R_SNK_C : 0);
         } else m << "0 0\n";
         k++;
     }
@@ -106,6 +117,11 @@ static void dump_tiles(G& graph) {
     for (uint32_t i = 0; i < A->J.size(); i++) {
         write_raw(base + ".J" + std::to_string(i) + ".bin", A->J[i].data(), A->J[i].size());
         write_raw(base + ".JV" + std::to_string(i) + ".bin", A->JV[i].data(), A->JV[i].size());
+    }
+    if (A->compression_type == _TCSC_CF_) {          /* classify_vertices (src/mat/matrix.hpp:1124-1144,853-855): the owned segment's lists */
+        write_raw(base + ".regrows.bin", A->rowgrp_regular_rows.data(), A->rowgrp_regular_rows.size());
+        write_raw(base + ".srcrows.bin", A->rowgrp_source_rows.data(), A->rowgrp_source_rows.size());
+        write_raw(base + ".snkcols.bin", A->colgrp_sink_columns.data(), A->colgrp_sink_columns.size());
     }
     std::ofstream lay(base + ".layout");
     lay << "local_row_segments";
