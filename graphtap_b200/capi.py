@@ -52,6 +52,10 @@ class TileView(C.Structure):
                 ("JA", C.c_void_p), ("IA", C.c_void_p), ("A", C.c_void_p), ("JC", C.c_void_p), ("IR", C.c_void_p)]
 
 
+class TileCfView(C.Structure):
+    _fields_ = [("NC", C.c_uint32 * 4), ("filled", C.c_uint32 * 4), ("JA", C.c_void_p * 4), ("JC", C.c_void_p * 4)]
+
+
 class Params(C.Structure):
     _fields_ = [("alpha", C.c_double), ("tol", C.c_double), ("root", C.c_uint32)]
 
@@ -59,7 +63,7 @@ class Params(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("execute_ms", C.c_double), ("scatter_gather_ms", C.c_double), ("combine_ms", C.c_double),
                 ("apply_ms", C.c_double), ("kernel_launches", C.c_uint64), ("bytes_algorithmic", C.c_uint64),
-                ("iterations", C.c_uint32), ("sparse_iterations", C.c_uint32)]
+                ("iterations", C.c_uint32), ("sparse_iterations", C.c_uint32), ("combine_bytes", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/graphtap_b200.h declares
@@ -92,6 +96,9 @@ PROTOTYPES = {
     "gt_graph_rowgrp_maps": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "gt_graph_colgrp_maps": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     "gt_graph_classify": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "gt_graph_classify_lists": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32),
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    "gt_graph_tile_cf_view": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(TileCfView)]),
     "gt_tile_spmv": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gt_tile_spmspv": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gt_program_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params), C.POINTER(C.c_void_p)]),

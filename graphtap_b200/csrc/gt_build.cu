@@ -194,10 +194,21 @@ __global__ void k_seg_maps(const uint8_t* bits_all, const uint32_t* scan_all, ui
     }
 }
 
-// hot order: key = (~degree, local id) for vertices with a non-empty row or column, all-ones otherwise
-__global__ void k_hot_keys(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, const uint32_t* __restrict__ deg, uint32_t th, uint64_t* __restrict__ keys) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
-        keys[i] = (I[i] | J[i]) ? (((uint64_t) (0xffffffffu - deg[i]) << 32) | i) : ~0ull;
+// hot order: key = (class, ~degree, local id) for vertices with a non-empty row or column, all-ones otherwise.
+// class (only on _TCSC_CF_ graphs, else 0 for everyone): 0 regular, 1 source row, 2 sink column.
+__global__ void k_hot_keys(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, const uint32_t* __restrict__ deg, uint32_t th, int cf,
+                           uint64_t* __restrict__ keys, uint8_t* __restrict__ cls, unsigned int* __restrict__ counts) {
+    unsigned int nreg = 0, nsrc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        const bool r = I[i], c = J[i];
+        const uint32_t d = min(deg[i], 0x3fffffffu);
+        const uint64_t k = (cf && !(r && c)) ? (r ? 1ull : 2ull) : 0ull;
+        keys[i] = (r || c) ? ((k << 62) | ((uint64_t) (0x3fffffffu - d) << 32) | i) : ~0ull;
+        if (cls) cls[i] = (uint8_t) (r && c ? 1 : r ? 2 : c ? 3 : 0);       // matrix.hpp:1135-1144
+        nreg += r && c; nsrc += r && !c;
+    }
+    if (nreg) atomicAdd(counts, nreg);
+    if (nsrc) atomicAdd(counts + 1, nsrc);
 }
 __global__ void k_hot_count(const uint64_t* __restrict__ keys, uint32_t th, uint32_t* __restrict__ n) {
     uint32_t lo = 0, hi = th;                      // first all-ones key (degrees are >= 1, so real keys are smaller)
@@ -277,6 +288,181 @@ static int bits_for(uint32_t v) {   // bits needed to represent values in [0, v)
     int b = 1;
     while (b < 32 && (1ull << b) < v) b++;
     return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// _TCSC_CF_: TCSC_CF_BASE::populate on the device (src/ds/compressed_column.hpp:671-1114)
+// ---------------------------------------------------------------------------------------------
+// F[e] = 1 iff entry e sits in a source row (row non-empty, column empty) of the tile's row group
+__global__ void k_cf_flags(const uint32_t* __restrict__ IA, uint64_t nnz, const uint32_t* __restrict__ IR, const uint8_t* __restrict__ rcls, uint8_t* __restrict__ F) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e <= nnz; e += (uint64_t) gridDim.x * blockDim.x)
+        F[e] = e < nnz ? (rcls[IR[IA[e]]] == 2) : 0;
+}
+struct U8ToU32 { __host__ __device__ uint32_t operator()(const uint8_t& v) const { return v; } };
+__device__ __forceinline__ uint32_t cf_col_of(const uint32_t* __restrict__ JA, uint32_t ncols, uint64_t e) {
+    uint32_t lo = 0, hi = ncols;                      // upper_bound(JA, e) - 1 = the column that holds entry e
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((uint64_t) JA[mid] <= e) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+// Stable partition permutation of every column: P[JA[j] + rho] = position of the column's rho-th regular entry,
+// P[JA[j] + B + sigma] = position of its sigma-th source entry (B = number of regular entries); S = exclusive scan of F.
+__global__ void k_cf_partition(const uint32_t* __restrict__ JA, uint32_t ncols, uint64_t nnz, const uint8_t* __restrict__ F, const uint32_t* __restrict__ S,
+                               uint32_t* __restrict__ P) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < nnz; e += (uint64_t) gridDim.x * blockDim.x) {
+        const uint32_t j = cf_col_of(JA, ncols, e);
+        const uint32_t b = JA[j], en = JA[j + 1];
+        const uint32_t nsrc = S[en] - S[b], B = (en - b) - nsrc, sigma = S[e] - S[b];
+        if (F[e]) P[b + B + sigma] = (uint32_t) e; else P[b + ((uint32_t) e - b - sigma)] = (uint32_t) e;
+    }
+}
+// "Moving source rows to the end" (:671-708) in closed form.  The reference walks the column's source entries in
+// ascending position and swaps each with the LAST regular entry still to its right; with B regular entries that pairs
+// the i-th source among the first B positions with the regular entry of rank B-1-i, and leaves everything else alone.
+__global__ void k_cf_swap(const uint32_t* __restrict__ JA, uint32_t ncols, uint64_t nnz, const uint8_t* __restrict__ F, const uint32_t* __restrict__ S,
+                          const uint32_t* __restrict__ P, const uint32_t* __restrict__ IA, const uint32_t* __restrict__ A,
+                          uint32_t* __restrict__ IA_out, uint32_t* __restrict__ A_out) {
+    for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < nnz; e += (uint64_t) gridDim.x * blockDim.x) {
+        if (!F[e]) continue;
+        const uint32_t j = cf_col_of(JA, ncols, e);
+        const uint32_t b = JA[j], en = JA[j + 1];
+        const uint32_t nsrc = S[en] - S[b], B = (en - b) - nsrc, sigma = S[e] - S[b];
+        if ((uint32_t) e - b >= B) continue;            // already in the tail
+        const uint32_t t = P[b + B - 1 - sigma];
+        IA_out[e] = IA[t]; IA_out[t] = IA[e];
+        if (A) { A_out[e] = A[t]; A_out[t] = A[e]; }
+    }
+}
+// per compressed column: which of the four lists it joins (bit k = kind k), and its source-entry count
+__global__ void k_cf_col_kinds(const uint32_t* __restrict__ JA, uint32_t ncols, const uint32_t* __restrict__ S, const uint32_t* __restrict__ JC,
+                               const uint8_t* __restrict__ ccls, uint8_t* __restrict__ kind0, uint8_t* __restrict__ kind1, uint8_t* __restrict__ kind2,
+                               uint8_t* __restrict__ kind3, unsigned long long* __restrict__ snk_src_edges) {
+    unsigned long long local = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) {
+        const uint32_t b = JA[j], en = JA[j + 1], len = en - b, nsrc = S[en] - S[b];
+        const uint8_t c = ccls[JC[j]];
+        const bool local_col = len > 0, reg = c == 1, snk = c == 3;
+        kind0[j] = local_col && reg && nsrc < len;      // :749-833
+        kind1[j] = local_col && snk && nsrc < len;      // :862-946
+        kind2[j] = local_col && reg && nsrc > 0;        // :949-1022
+        kind3[j] = local_col && snk && nsrc > 0;        // :1025-1108
+        if (local_col && snk) local += nsrc;            // NC_SRC_R_SNK_C counts EDGES (:1046-1049)
+    }
+    if (local) atomicAdd(snk_src_edges, local);
+}
+__global__ void k_cf_pairs(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ S, const uint32_t* __restrict__ JCk, uint32_t n, int kind,
+                           uint32_t* __restrict__ JAk) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t j = JCk[i];
+        const uint32_t b = JA[j], en = JA[j + 1], nsrc = S[en] - S[b];
+        uint32_t lo, hi;
+        if (kind <= 1) { lo = b; hi = en - nsrc; }      // regular rows of the column
+        else if (kind == 2) { lo = en - nsrc; hi = en; }
+        else { lo = b + nsrc; hi = en; }                // the reference's own start (:1094)
+        JAk[2 * i] = lo; JAk[2 * i + 1] = hi;
+    }
+}
+__global__ void k_cf_owned(const uint8_t* __restrict__ cls, uint32_t th, uint8_t* __restrict__ reg, uint8_t* __restrict__ src, uint8_t* __restrict__ snk) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
+        const uint8_t c = cls[i];
+        reg[i] = c == 1; src[i] = c == 2; snk[i] = c == 3;
+    }
+}
+
+static uint32_t select_flagged(gt_ctx* ctx, const uint8_t* flags, uint32_t n, DevBuf<uint32_t>& out, uint32_t min_alloc = 0) {
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint32_t> tmp_out; tmp_out.alloc(std::max<uint32_t>(n, 1));
+    DevBuf<unsigned int> d_n; d_n.alloc(1);
+    size_t tb = 0;
+    cub::CountingInputIterator<uint32_t> it(0);
+    GT_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, it, flags, tmp_out.p, d_n.p, (int) n, st));
+    DevBuf<uint8_t> tmp; tmp.alloc(tb);
+    GT_CUDA(cub::DeviceSelect::Flagged(tmp.p, tb, it, flags, tmp_out.p, d_n.p, (int) n, st));
+    unsigned int h = 0;
+    GT_CUDA(cudaMemcpyAsync(&h, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    out.alloc(std::max<uint32_t>(std::max(h, min_alloc), 1));
+    GT_CUDA(cudaMemsetAsync(out.p, 0, out.bytes(), st));
+    if (h) GT_CUDA(cudaMemcpyAsync(out.p, tmp_out.p, (size_t) h * 4, cudaMemcpyDeviceToDevice, st));
+    GT_CUDA(cudaStreamSynchronize(st));
+    ctx->kernel_launches += 2;
+    return h;
+}
+
+static void build_cf(gt_graph* g) {
+    gt_ctx* ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t th = g->lay.info.tile_height;
+    // classify_vertices of the owned segment
+    {
+        const uint8_t* cls = g->cls[g->hot_of_row_slot[g->lay.info.accu_segment_row]].p;
+        DevBuf<uint8_t> f; f.alloc(3 * (size_t) th);
+        k_cf_owned<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(cls, th, f.p, f.p + th, f.p + 2 * (size_t) th);
+        ctx->kernel_launches++;
+        g->cf_owned.nreg = select_flagged(ctx, f.p, th, g->cf_owned.regular_rows);
+        g->cf_owned.nsrc = select_flagged(ctx, f.p + th, th, g->cf_owned.source_rows);
+        g->cf_owned.nsnk = select_flagged(ctx, f.p + 2 * (size_t) th, th, g->cf_owned.sink_columns);
+    }
+    g->cf_tiles.resize(g->tiles.size());
+    for (size_t k = 0; k < g->tiles.size(); k++) {
+        const Tile& T = g->tiles[k];
+        CfTile& C = g->cf_tiles[k];
+        if (!T.nnz) continue;
+        const SegMaps& R = g->rows[T.row_slot];
+        const SegMaps& Cs = g->cols[T.col_slot];
+        const uint8_t* rcls = g->cls[g->hot_of_row_slot[T.row_slot]].p;
+        const uint8_t* ccls = g->cls[g->hot_of_col_slot[T.col_slot]].p;
+        uint32_t* IA = g->IA_pool.p + T.offset;
+        uint32_t* A = g->weighted ? g->A_pool.p + T.offset : nullptr;
+        const uint32_t ncols = Cs.nnz;
+        DevBuf<uint8_t> F; F.alloc(T.nnz + 1);
+        DevBuf<uint32_t> S; S.alloc(T.nnz + 1);
+        k_cf_flags<<<grid_for(T.nnz + 1, 256, ctx->sm_count, 16), 256, 0, st>>>(IA, T.nnz, R.ids.p, rcls, F.p);
+        {
+            size_t tb = 0;
+            cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t*> in(F.p, U8ToU32());
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, S.p, (int64_t) T.nnz + 1, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, S.p, (int64_t) T.nnz + 1, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        {   // IA (and A) in the reference's order
+            DevBuf<uint32_t> P, IA2, A2;
+            P.alloc(T.nnz); IA2.alloc(T.nnz);
+            if (A) A2.alloc(T.nnz);
+            k_cf_partition<<<grid_for(T.nnz, 256, ctx->sm_count, 16), 256, 0, st>>>(T.JA.p, ncols, T.nnz, F.p, S.p, P.p);
+            GT_CUDA(cudaMemcpyAsync(IA2.p, IA, T.nnz * 4, cudaMemcpyDeviceToDevice, st));
+            if (A) GT_CUDA(cudaMemcpyAsync(A2.p, A, T.nnz * 4, cudaMemcpyDeviceToDevice, st));
+            k_cf_swap<<<grid_for(T.nnz, 256, ctx->sm_count, 16), 256, 0, st>>>(T.JA.p, ncols, T.nnz, F.p, S.p, P.p, IA, A, IA2.p, A ? A2.p : nullptr);
+            GT_CUDA(cudaMemcpyAsync(IA, IA2.p, T.nnz * 4, cudaMemcpyDeviceToDevice, st));
+            if (A) GT_CUDA(cudaMemcpyAsync(A, A2.p, T.nnz * 4, cudaMemcpyDeviceToDevice, st));
+            GT_CUDA(cudaGetLastError());
+            GT_CUDA(cudaStreamSynchronize(st));
+        }
+        // the four lists
+        DevBuf<uint8_t> kinds; kinds.alloc(4 * (size_t) std::max<uint32_t>(ncols, 1));
+        DevBuf<unsigned long long> d_e; d_e.alloc(1);
+        GT_CUDA(cudaMemsetAsync(d_e.p, 0, 8, st));
+        k_cf_col_kinds<<<grid_for(ncols, 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, ncols, S.p, Cs.ids.p, ccls, kinds.p, kinds.p + ncols, kinds.p + 2 * (size_t) ncols,
+                                                                          kinds.p + 3 * (size_t) ncols, d_e.p);
+        unsigned long long snk_src_edges = 0;
+        GT_CUDA(cudaMemcpyAsync(&snk_src_edges, d_e.p, 8, cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaStreamSynchronize(st));
+        for (int kind = 0; kind < 4; kind++) {
+            const uint32_t want = kind == 3 ? (uint32_t) snk_src_edges : 0;      // NC_SRC_R_SNK_C is an edge count; the tail stays zero
+            C.filled[kind] = select_flagged(ctx, kinds.p + (size_t) kind * ncols, ncols, C.JC[kind], want);
+            C.NC[kind] = kind == 3 ? want : C.filled[kind];
+            C.JA[kind].alloc(2 * (size_t) std::max<uint32_t>(C.NC[kind], 1));
+            GT_CUDA(cudaMemsetAsync(C.JA[kind].p, 0, C.JA[kind].bytes(), st));
+            if (C.filled[kind])
+                k_cf_pairs<<<grid_for(C.filled[kind], 256, ctx->sm_count), 256, 0, st>>>(T.JA.p, S.p, C.JC[kind].p, C.filled[kind], kind, C.JA[kind].p);
+        }
+        ctx->kernel_launches += 8;
+        GT_CUDA(cudaGetLastError());
+        GT_CUDA(cudaStreamSynchronize(st));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -472,17 +658,25 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
             GT_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (int64_t) th, 0, 64, st));
             tmp.alloc(tb);
         }
-        DevBuf<uint32_t> d_n; d_n.alloc(1);
+        DevBuf<uint32_t> d_n; d_n.alloc(3);
+        const int cf = compression == GT_TCSC_CF;
+        if (cf) g->cls.resize(segs.size());
         for (size_t h = 0; h < segs.size(); h++) {
             HotOrder& H = g->hot[h];
             H.segment = segs[h];
             const uint64_t b = (uint64_t) segs[h] * th;
-            k_hot_keys<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(I_all.p + b, J_all.p + b, deg_all.p + b, th, keys.p);
+            if (cf) g->cls[h].alloc(th);
+            GT_CUDA(cudaMemsetAsync(d_n.p, 0, 12, st));
+            k_hot_keys<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(I_all.p + b, J_all.p + b, deg_all.p + b, th, cf, keys.p, cf ? g->cls[h].p : nullptr, d_n.p + 1);
             cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
             GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) th, 0, 64, st));
             k_hot_count<<<1, 1, 0, st>>>(db.Current(), th, d_n.p);
-            GT_CUDA(cudaMemcpyAsync(&H.n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+            uint32_t h_n[3];
+            GT_CUDA(cudaMemcpyAsync(h_n, d_n.p, 12, cudaMemcpyDeviceToHost, st));
             GT_CUDA(cudaStreamSynchronize(st));
+            H.n = h_n[0];
+            H.nreg = cf ? h_n[1] : H.n;
+            H.nsrc = cf ? h_n[2] : 0;
             H.ids.alloc(H.n); H.pos.alloc(th);
             GT_CUDA(cudaMemsetAsync(H.pos.p, 0xff, (size_t) th * 4, st));
             if (H.n) k_hot_finish<<<grid_for(H.n, 256, ctx->sm_count), 256, 0, st>>>(db.Current(), H.n, H.ids.p, H.pos.p);
@@ -557,6 +751,8 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
         GT_CUDA(cudaStreamSynchronize(st));
         for (int k = 0; k < ntiles; k++) g->tiles[k].max_col_entries = h_m[k];
     }
+
+    if (compression == GT_TCSC_CF) build_cf(g.get());
 
     // nnz over all ranks
     g->nnz_global = g->nnz_local;
@@ -674,6 +870,35 @@ extern "C" int gt_graph_classify(gt_graph* g, uint32_t* regular, uint32_t* sourc
         if (regular) *regular = h[0];
         if (source_rows) *source_rows = h[1];
         if (sink_columns) *sink_columns = h[2];
+    });
+}
+
+extern "C" int gt_graph_classify_lists(gt_graph* g, const uint32_t** regular_rows, uint32_t* nregular, const uint32_t** source_rows, uint32_t* nsource,
+                                       const uint32_t** sink_columns, uint32_t* nsink) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g, "gt_graph_classify_lists: NULL graph");
+        if (g->compression != GT_TCSC_CF)
+            throw gt::Error(GT_ERR_INVALID, "gt_graph_classify_lists: the graph was not built with GT_TCSC_CF (the reference keeps these lists for _TCSC_CF_ only)");
+        if (regular_rows) *regular_rows = g->cf_owned.regular_rows.p;
+        if (source_rows) *source_rows = g->cf_owned.source_rows.p;
+        if (sink_columns) *sink_columns = g->cf_owned.sink_columns.p;
+        if (nregular) *nregular = g->cf_owned.nreg;
+        if (nsource) *nsource = g->cf_owned.nsrc;
+        if (nsink) *nsink = g->cf_owned.nsnk;
+    });
+}
+
+extern "C" int gt_graph_tile_cf_view(gt_graph* g, uint32_t local_tile, gt_tile_cf_view* out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(g && out, "gt_graph_tile_cf_view: NULL argument");
+        GT_REQUIRE(local_tile < g->tiles.size(), "gt_graph_tile_cf_view: tile index out of range");
+        if (g->compression != GT_TCSC_CF)
+            throw gt::Error(GT_ERR_INVALID, "gt_graph_tile_cf_view: the graph was not built with GT_TCSC_CF");
+        const gt::CfTile& C = g->cf_tiles[local_tile];
+        for (int k = 0; k < 4; k++) {
+            out->NC[k] = C.NC[k]; out->filled[k] = C.filled[k];
+            out->JA[k] = C.JA[k].p; out->JC[k] = C.JC[k].p;
+        }
     });
 }
 

@@ -59,10 +59,12 @@ __global__ void k_messenger_f64(VState V, int app, const uint32_t* __restrict__ 
 }
 // ---- applicator ------------------------------------------------------------------------------------------
 // stationary, TCSC: rows with I[i] take y[j++] (here y[r] with v = IR[r]) (:1655-1670)
+// `cls` (PageRank on a _TCSC_CF_ graph): regular rows every iteration, source rows only on the last (:1671-1692)
 __global__ void k_apply_f64(VState V, int app, const uint32_t* __restrict__ IR, uint32_t nr, const double* __restrict__ y,
-                            double alpha, double tol) {
+                            double alpha, double tol, const uint8_t* __restrict__ cls, int last) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
         const uint32_t v = IR[r];
+        if (cls) { const uint8_t c = cls[v]; if (!(c == 1 || (c == 2 && last))) continue; }
         const double yy = y[r];
         if (app == GT_APP_DEG) { V.a[v] = (uint32_t) yy; V.C[v] = 0; continue; }           // deg.h:49-52
         const double old = V.rank[v];
@@ -76,9 +78,10 @@ __global__ void k_clear_C_empty(uint8_t* C, const uint8_t* __restrict__ I, uint3
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
         if (!I[i]) C[i] = 0;
 }
-__global__ void __launch_bounds__(256) k_count_u8(const uint8_t* __restrict__ C, uint32_t n, unsigned long long* __restrict__ out) {
+// has_converged: vertices still moving; on a _TCSC_CF_ graph only the regular rows count (:1902-1916)
+__global__ void __launch_bounds__(256) k_count_u8(const uint8_t* __restrict__ C, uint32_t n, const uint8_t* __restrict__ cls, unsigned long long* __restrict__ out) {
     unsigned local = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) local += C[i] ? 1 : 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) local += (C[i] && (!cls || cls[i] == 1)) ? 1 : 0;
     typedef cub::BlockReduce<unsigned, 256> BR;
     __shared__ typename BR::TempStorage tmp;
     const unsigned tot = BR(tmp).Sum(local);
@@ -136,6 +139,20 @@ __global__ void __launch_bounds__(256) k_pr_apply_h(const double* __restrict__ y
         const unsigned tot = BR(tmp).Sum(local);
         if (threadIdx.x == 0 && tot) atomicAdd(active, (unsigned long long) tot);
     }
+}
+
+// _TCSC_CF_ in convergence mode: after has_converged() the reference's combine() does nothing for this compression
+// (:1036-1043) and apply() then hands every SOURCE row the y left by the last iteration — zero, because only the
+// REG x REG list ran (:1282) — so the row ends at alpha + (1 - alpha) * 0 (:1683-1690).  Reproduced as is.
+__global__ void k_pr_cf_sources_h(double* __restrict__ rank_h, uint8_t* __restrict__ C_h, uint32_t lo, uint32_t hi, double alpha) {
+    for (uint32_t k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+        rank_h[k] = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, 0.0));
+        C_h[k] = 0;
+    }
+}
+__global__ void k_pr_cf_sources(VState V, const uint8_t* __restrict__ cls, uint32_t th, double alpha) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x)
+        if (cls[i] == 2) { V.rank[i] = __dadd_rn(alpha, __dmul_rn(1.0 - alpha, 0.0)); V.C[i] = 0; }
 }
 
 // initialize(other): degree hand-over where the row is non-empty (:476-483, pr.h:24-28)
@@ -334,6 +351,7 @@ static void prog_initialize(gt_program* P) {
         P->pull = P->g->pull;
         if (!P->pull_ready) pull_alloc(P);
     }
+    P->cf = P->app == GT_APP_PR && P->g->compression == GT_TCSC_CF && P->ordering == GT_ROW;
     P->hot_valid = false;
     P->x_ready = false;
     P->initialized = true;
@@ -342,18 +360,41 @@ static void prog_initialize(gt_program* P) {
     P->empty_cleared = false;
 }
 
-static uint64_t algorithmic_bytes_dense(const gt_program* P) {
-    // per tile IA (+A) + JA + one read of its x segment; per row group one write of y;
-    // vertex phase on the owned segment: JC + state read, IR + y + state read/write.
+// the running iteration's place in the computation-filtering schedule (:1246,1282): iteration 0 adds REG x SNK, the last
+// iteration of a fixed-count run adds the source rows; phases driven through run_phase() are a middle iteration
+static inline bool cf_first(const gt_program* P) { return P->cf && P->in_execute && P->iteration == 0; }
+static inline bool cf_last(const gt_program* P) { return P->cf && P->in_execute && !P->check_mode && P->iteration + 1 == P->num_iterations; }
+
+// SURVEY.md §8(d), one iteration: per tile IA (+A) + JA + one read of its x segment; per row group one write of y;
+// vertex phase on the owned segment: JC + state read, IR + y + state read/write.  On a _TCSC_CF_ graph the pull path
+// moves only what the schedule touches: the REG x REG entries (+ REG x SNK first, + source rows last), the regular part
+// of x and of y.  `combine_only`: without the vertex phase.
+static uint64_t algorithmic_bytes_iteration(const gt_program* P, bool first, bool last, bool combine_only) {
     const gt_graph* g = P->g;
     const uint64_t es = P->esize();
     uint64_t b = 0;
+    if (P->pull && P->pull->cf) {
+        const PullLayout* L = P->pull;
+        for (size_t k = 0; k < L->rows.size(); k++) {
+            const PullRows& Q = L->rows[k];
+            b += 4 * (Q.nnz_rr + (first ? Q.snk.nnz : 0) + (last ? Q.src.nnz : 0));
+            b += 8ull * (L->yreg[k] + (last ? L->ysrc[k] : 0));
+        }
+        for (size_t c = 0; c < L->xn.size(); c++)
+            b += (4 + 8) * (uint64_t) (L->xreg[c] + ((first || last) ? L->xn[c] - L->xsnk0[c] : 0)) * L->rows.size();   // column pointer + x, once per tile of the column
+        if (!combine_only) {
+            const HotOrder& H = *P->own_hot;
+            b += (4 + 12) * (uint64_t) H.nreg + (4 + 8 + 16) * (uint64_t) (H.nreg + (last ? H.nsrc : 0));
+        }
+        return b;
+    }
     for (const Tile& T : g->tiles) {
         const uint64_t nc = (P->ordering == GT_ROW ? g->cols[T.col_slot].nnz : g->rows[T.row_slot].nnz);
         if (!T.nnz) continue;
         b += (g->weighted ? 8 : 4) * T.nnz + 4 * ((uint64_t) g->cols[T.col_slot].nnz + 1) + es * nc;
     }
     for (const SegMaps& r : *P->prow) b += es * r.nnz;
+    if (combine_only) return b;
     const uint64_t state = (P->app == GT_APP_PR) ? 12 : 4;
     b += (4 + state) * (uint64_t) (*P->pcol)[P->own_col_slot].nnz;
     b += (4 + es + (P->app == GT_APP_PR ? 16 : 8)) * (uint64_t) (*P->prow)[P->own_row_slot].nnz;
@@ -410,23 +451,37 @@ static void pull_scatter_gather(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     pull_state_in(P);
+    const PullLayout* L = P->pull;
     const uint32_t n = P->own_hot->n;
-    double* xo = pull_x_next(P) + P->pull->xoff[P->own_col_slot];
-    if (!P->x_ready && n) {                           // later iterations: x was written by the fused applicator
+    const uint32_t xo_off = L->xoff[P->own_col_slot];
+    double* xo = pull_x_next(P) + xo_off;
+    // Computation filtering: after the first exchange only the REGULAR part of x changes (the applicator writes nothing
+    // else), and the sink columns' x — constant, their vertices have no row and are never applied — must sit in both
+    // parity buffers.  So the first exchange of an execute() ships the whole chunk and the sink range twice.
+    const bool first = !P->x_ready;
+    const uint32_t snk0 = L->xsnk0[P->own_col_slot], nsnk = n - std::min(n, snk0);
+    double* xo_other = P->wx ? P->xbuf[P->x_epoch & 1] + xo_off : nullptr;       // the parity the next exchange does NOT use
+    if (first && n) {                                 // later iterations: x was written by the fused applicator
         k_pr_messenger_h<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(P->rank_h.p, P->deg_h.p, n, xo);
         ctx->kernel_launches++;
+        if (L->cf && xo_other && nsnk) GT_CUDA(cudaMemcpyAsync(xo_other + snk0, xo + snk0, (size_t) nsnk * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     P->x_ready = true;
     P->ag_pending = false;
+    const uint32_t nput = (L->cf && !first) ? P->own_hot->nreg : n;
     if (P->wx) {
         // bcast_stationary (:843-862) as puts: the own chunk goes into every other member's window by copy engine,
-        // on the side stream, while this rank's SpMV over its own chunk is already running
+        // on the side streams, while this rank's SpMV over its own chunk is already running
         P->x_epoch++;
         GT_CUDA(cudaEventRecord(ctx->ev_x, st));
         peer_put_begin(ctx, ctx->ev_x);
-        const size_t off = ((size_t) (P->x_epoch & 1) * P->x_stride + P->pull->xoff[P->own_col_slot]) * sizeof(double);
-        for (int j = 1; j < P->wx->size; j++)
-            peer_put(ctx, P->wx, (P->wx->me + j) % P->wx->size, off, xo, (size_t) n * sizeof(double), P->x_epoch);
+        const size_t off = ((size_t) (P->x_epoch & 1) * P->x_stride + xo_off) * sizeof(double);
+        const size_t off_other = ((size_t) ((P->x_epoch + 1) & 1) * P->x_stride + xo_off + snk0) * sizeof(double);
+        for (int j = 1; j < P->wx->size; j++) {
+            const int q = (P->wx->me + j) % P->wx->size;
+            if (first && L->cf && nsnk) peer_put(ctx, P->wx, q, off_other, xo + snk0, (size_t) nsnk * sizeof(double), P->x_epoch, false);
+            peer_put(ctx, P->wx, q, off, xo, (size_t) nput * sizeof(double), P->x_epoch);
+        }
         peer_put_end(ctx, nullptr);
         P->x_wait_pending = true;
     } else if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
@@ -454,16 +509,27 @@ static void pull_combine(gt_program* P) {
     const double* x = pull_x_cur(P);
     const size_t R = L->rows.size();
     const size_t own = (size_t) P->own_row_slot;
+    const bool first = cf_first(P), last = cf_last(P);
+    P->combine_bytes = algorithmic_bytes_iteration(P, first, last, true);
     if (P->ypush_pending) { peer_puts_done(ctx, P->ev_yput, st); P->ypush_pending = false; }   // the last puts have read Yh
     if (P->Yh.n) GT_CUDA(cudaMemsetAsync(P->Yh.p, 0, P->Yh.bytes(), st));     // std::fill(y, 0) (:1026-1032)
+    // everything of a row segment that needs the other members' x: the rest of REG x REG every iteration, REG x SNK in
+    // iteration 0 (:1246-1262), the source rows in the last one (:1282-1317)
+    auto remote_parts = [&](size_t k) {
+        double* y = P->Yh.p + L->yoff[k];
+        pull_spmv(ctx, L, (uint32_t) k, 1, x, y);
+        if (first) pull_spmv(ctx, L, (uint32_t) k, 2, x, y);
+        if (last) pull_spmv(ctx, L, (uint32_t) k, 3, x, y);
+    };
     // Row segments led by other ranks first: their partial y leaves for the leader while the owned segment is computed.
     // Part 0 needs only this rank's own x chunk, so it runs while the other chunks are still arriving.
     for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) pull_spmv(ctx, L, (uint32_t) k, 0, x, P->Yh.p + L->yoff[k]);
     if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 0, x, P->Yh.p + L->yoff[own]);
     pull_x_arrived(P);
-    for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) pull_spmv(ctx, L, (uint32_t) k, 1, x, P->Yh.p + L->yoff[k]);
+    for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) remote_parts(k);
     if (P->wy) {
-        // combine_2d_stationary's follower -> leader sends (:1083-1108) as puts into slot `me` of the leader's window
+        // combine_2d_stationary's follower -> leader sends (:1083-1108) as puts into slot `me` of the leader's window;
+        // with computation filtering only the rows the leader will apply: the regular ones, plus the source rows at the end
         P->y_epoch++;
         GT_CUDA(cudaEventRecord(P->ev_b, st));
         peer_put_begin(ctx, P->ev_b);
@@ -472,12 +538,13 @@ static void pull_combine(gt_program* P) {
             if (k == own) continue;
             const int q = (int) (L->yoff[k] / L->ychunk);                       // group rank of the segment's leader
             const size_t off = ((size_t) (P->y_epoch & 1) * G + P->wy->me) * L->ychunk * sizeof(double);
-            peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) L->yn[k] * sizeof(double), P->y_epoch);
+            const uint32_t ny = L->cf ? L->yreg[k] + (last ? L->ysrc[k] : 0) : L->yn[k];
+            peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) ny * sizeof(double), P->y_epoch);
         }
         peer_put_end(ctx, P->ev_yput);
         P->ypush_pending = true;
     }
-    if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 1, x, P->Yh.p + L->yoff[own]);
+    if (L->yn[own]) remote_parts(own);
     if (P->wy) peer_wait_all(ctx, P->wy, P->y_epoch, st);                       // the followers' partials of the owned segment
     else if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
         comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, L->ychunk, CT_F64, CO_SUM, st);
@@ -487,7 +554,9 @@ static void pull_apply(gt_program* P, bool count_active) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     const PullLayout* L = P->pull;
-    const uint32_t n = P->own_hot->n;
+    // apply_stationary's _TCSC_CF_ branch (:1671-1692): the regular rows every iteration, the source rows on the last one;
+    // the positions beyond (sink columns: no row) are never applied and their x never changes
+    const uint32_t n = L->cf ? P->own_hot->nreg + (cf_last(P) ? P->own_hot->nsrc : 0) : P->own_hot->n;
     if (count_active) GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
     if (n) {
         YParts yr{};
@@ -521,6 +590,7 @@ static void combine(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
     gt_graph* g = P->g;
+    P->combine_bytes = algorithmic_bytes_iteration(P, false, false, true);
     GT_CUDA(cudaMemsetAsync(P->Ycat.p, 0, P->Ycat.n, st));     // std::fill(y, 0) (:1026-1032)
     // The reference walks local_tiles_row_order (_ROW_) or local_tiles_col_order (_COL_); the order only
     // fixes when a segment's partial is shipped, which the grouped reduce below does for all at once.
@@ -545,7 +615,11 @@ static void apply(gt_program* P, bool count_active = false) {
         P->empty_cleared = true;
     }
     if (own.nnz) {
-        k_apply_f64<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha, P->prm.tol);
+        // push path on a _TCSC_CF_ graph: the SpMV covers every entry each iteration (sink columns carry x = 0 under the
+        // reference's drivers, so y is the same), the applicator and the convergence test follow the CF row classes
+        const uint8_t* cls = P->cf ? P->g->cls[P->g->hot_of_row_slot[P->own_row_slot]].p : nullptr;
+        k_apply_f64<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, own.ids.p, own.nnz, (const double*) P->Y[P->own_row_slot].p, P->prm.alpha,
+                                                                         P->prm.tol, cls, cf_last(P));
         ctx->kernel_launches++;
     }
     GT_CUDA(cudaGetLastError());
@@ -557,7 +631,8 @@ static void has_converged_begin(gt_program* P) {
     cudaStream_t st = ctx->stream;
     if (!P->pull) {
         GT_CUDA(cudaMemsetAsync(P->d_active.p, 0, sizeof(unsigned long long), st));
-        k_count_u8<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, P->th, P->d_active.p);
+        const uint8_t* cls = P->cf ? P->g->cls[P->g->hot_of_row_slot[P->own_row_slot]].p : nullptr;
+        k_count_u8<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, P->th, cls, P->d_active.p);
         ctx->kernel_launches++;
     }
     if (ctx->comm) comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p, P->d_active.p, 1, CT_U64, CO_SUM, st);
@@ -659,8 +734,8 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         if (!p->stationary) {
             gt::ns_execute(p, num_iterations);            // records ev1, drains the stream
         } else {
-            const uint64_t dense_bytes = gt::algorithmic_bytes_dense(p);
             const bool peer_used = p->wx || p->wy;
+            p->in_execute = true; p->check_mode = check; p->num_iterations = num_iterations;
             // the members of a group may enter execute() far apart (one still building its pull layout): meet once, on the
             // device, before the first arrival counter is polled, so the poll timeout only ever measures a real stall
             if (peer_used) gt::peer_fence_world(ctx, ctx->stream);
@@ -677,14 +752,24 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
             while (true) {
                 phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
                 phase(p->tm.combine_ms, [&] { gt::combine(p); });
+                p->tm.bytes_algorithmic += gt::algorithmic_bytes_iteration(p, gt::cf_first(p), gt::cf_last(p), false);
                 phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
                 p->iteration++;
-                p->tm.bytes_algorithmic += dense_bytes;   // every stationary iteration moves the full structure
                 if (check) {
                     gt::has_converged_begin(p);
                     p->converged = gt::has_converged_end(p);
-                    if (p->converged) break;              // the post-convergence combine()+apply() (:425-429) changes no state for TCSC
+                    if (p->converged) break;              // the post-convergence combine()+apply() (:425-429) changes no state for _TCSC_ ...
                 } else if (p->iteration >= num_iterations) break;
+            }
+            p->in_execute = false;
+            if (p->cf && check && p->converged) {         // ... and leaves the source rows of a _TCSC_CF_ graph at alpha (see k_pr_cf_sources)
+                if (p->pull) {
+                    const uint32_t lo = p->own_hot->nreg, hi = lo + p->own_hot->nsrc;
+                    if (hi > lo) { gt::k_pr_cf_sources_h<<<gt::grid_for(hi - lo, 256, ctx->sm_count), 256, 0, ctx->stream>>>(p->rank_h.p, p->C_h.p, lo, hi, p->prm.alpha); ctx->kernel_launches++; }
+                } else {
+                    gt::k_pr_cf_sources<<<gt::grid_for(p->th, 256, ctx->sm_count), 256, 0, ctx->stream>>>(p->vs(), p->g->cls[p->g->hot_of_row_slot[p->own_row_slot]].p, p->th, p->prm.alpha);
+                    ctx->kernel_launches++;
+                }
             }
             if (p->pull) { gt::pull_x_arrived(p); gt::pull_state_out(p); }   // hot-order working state -> V (one pass per execute, inside the timed window)
             GT_CUDA(cudaEventRecord(p->ev1, ctx->stream));
@@ -808,6 +893,7 @@ extern "C" int gt_program_checksum(gt_program* p, uint64_t* value_sum, uint64_t*
 extern "C" int gt_program_timing(gt_program* p, gt_timing* out) {
     return gt::guarded([&] {
         GT_REQUIRE(p && out, "gt_program_timing: NULL argument");
+        p->tm.combine_bytes = p->combine_bytes;
         *out = p->tm;
     });
 }

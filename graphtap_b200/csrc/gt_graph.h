@@ -18,9 +18,13 @@ struct SegMaps {
 // decreasing global degree (in + out, counted at ingest over the whole edge list, so every rank derives
 // the same order without communication).  The pull layout of the plus-times SpMV indexes both x and y of
 // the segment in this order (gt_pull.cu).
+// On a _TCSC_CF_ graph the order is by vertex class first — regular (row and column non-empty), then source rows (row
+// only), then sink columns (column only), src/mat/matrix.hpp:1135-1144 — and by degree inside a class, so the three
+// sets the computation-filtering schedule treats differently are three contiguous ranges of every x and y vector.
 struct HotOrder {
     int32_t segment = -1;
     uint32_t n = 0;                // vertices in the order
+    uint32_t nreg = 0, nsrc = 0;   // _TCSC_CF_: [0, nreg) regular, [nreg, nreg + nsrc) source rows, the rest sink columns; else nreg = n
     DevBuf<uint32_t> ids;          // [n]           position -> local vertex id
     DevBuf<uint32_t> pos;          // [tile_height] local vertex id -> position, 0xffffffff if absent
 };
@@ -32,6 +36,18 @@ struct Tile {
     DevBuf<uint32_t> JA;           // [cols[col_slot].nnz + 1]
     DevBuf<uint32_t> chunk_col;    // first column of every GT_PUSH_CHUNK-edge chunk (+ sentinel)
     uint32_t max_col_entries = 0;  // longest column of the tile (decides whether the heavy-column path can trigger)
+};
+
+// TCSC_CF_BASE's computation-filtering lists of one tile (src/ds/compressed_column.hpp:749-1114):
+// kind 0 REG_R_REG_C, 1 REG_R_SNK_C, 2 SRC_R_REG_C, 3 SRC_R_SNK_C; NC pairs (start, end) into IA + NC compressed column ids.
+struct CfTile {
+    uint32_t NC[4] = {0, 0, 0, 0}, filled[4] = {0, 0, 0, 0};
+    DevBuf<uint32_t> JA[4], JC[4];
+};
+// classify_vertices of the owned segment (src/mat/matrix.hpp:1124-1144, :853-855): local vertex ids
+struct CfOwned {
+    DevBuf<uint32_t> regular_rows, source_rows, sink_columns;
+    uint32_t nreg = 0, nsrc = 0, nsnk = 0;
 };
 
 struct PullLayout;
@@ -52,6 +68,9 @@ struct gt_graph {
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
     gt::DevBuf<uint2> heavy_list;            // frontier SpMSpV scratch: (frontier position, chunk) of heavy columns + a counter
     gt::DevBuf<unsigned int> heavy_count;
+    std::vector<gt::CfTile> cf_tiles;        // _TCSC_CF_ only, parallel to `tiles`
+    gt::CfOwned cf_owned;                    // _TCSC_CF_ only
+    std::vector<gt::DevBuf<uint8_t>> cls;    // _TCSC_CF_ only, per distinct local segment (same index as `hot`): 1 regular, 2 source row, 3 sink column
     std::vector<gt::HotOrder> hot;           // one per distinct local segment
     std::vector<int> hot_of_row_slot, hot_of_col_slot;
     gt::PullLayout* pull = nullptr;          // derived layout of the plus-times SpMV, built on first use (gt_pull.cu)

@@ -143,12 +143,12 @@ void peer_put_begin(gt_ctx* ctx, cudaEvent_t ready) {
     for (int i = 0; i < ctx->peer_lanes; i++) GT_CUDA(cudaStreamWaitEvent(ctx->put_stream[i], ready, 0));
 }
 
-void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value) {
+void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value, bool advance) {
     GT_REQUIRE(dst_offset + bytes <= w->data_bytes, "peer exchange: put outside the window");
     const int d = (dst_member - w->me - 1 + w->size) % w->size;          // 0 .. size-2: which of my destinations this is
     cudaStream_t s = ctx->put_stream[d % ctx->peer_lanes];
     if (bytes) GT_CUDA(cudaMemcpyAsync(w->remote[dst_member] + dst_offset, src, bytes, cudaMemcpyDefault, s));
-    GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me), ctx->peer_seq.p + (value & (kPeerSeqLen - 1)), 4, cudaMemcpyDefault, s));
+    if (advance) GT_CUDA(cudaMemcpyAsync(w->flag(dst_member, w->me), ctx->peer_seq.p + (value & (kPeerSeqLen - 1)), 4, cudaMemcpyDefault, s));
 }
 
 void peer_put_end(gt_ctx* ctx, cudaEvent_t* done) {

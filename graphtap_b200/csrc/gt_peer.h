@@ -31,7 +31,8 @@ void peer_put_begin(gt_ctx* ctx, cudaEvent_t ready);
 // this rank <- value on the same stream, so the counter lands after the payload.  Every destination has its own
 // stream (GT_PEER_LANES of them, default 4), so the puts to the 3 column-group peers at p = 8 are driven by different
 // copy engines at the same time instead of queueing behind each other.
-void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value);
+// `advance` = false: payload only, the counter stays (an extra piece that a later put on the same stream publishes)
+void peer_put(gt_ctx* ctx, const PeerWindow* w, int dst_member, size_t dst_offset, const void* src, size_t bytes, uint32_t value, bool advance = true);
 void peer_put_end(gt_ctx* ctx, cudaEvent_t* done);
 void peer_puts_done(gt_ctx* ctx, cudaEvent_t* done, cudaStream_t s);
 // blocks `s` (on the device) until every other member's counters in the local window have reached `value`

@@ -73,6 +73,11 @@ struct gt_program {
     const gt::HotOrder* own_hot = nullptr;
     gt::DevBuf<uint32_t> stage;                    // AoS staging of V for gt_program_state_{to,from}_host (kept: no malloc per call)
     bool hot_valid = false, x_ready = false, ag_pending = false;
+    // _TCSC_CF_ graphs: the computation-filtering schedule of the running execute() (vertex_program.hpp:1218-1325,1671-1692)
+    bool cf = false;                               // PageRank on a GT_TCSC_CF graph
+    bool in_execute = false, check_mode = false;
+    uint32_t num_iterations = 0;
+    uint64_t combine_bytes = 0;                    // algorithmic bytes of the most recent combine phase
     // ---- non-stationary programs (gt_ns.cu) ------------------------------------------------------------------
     gt::NsState* ns = nullptr;
     // ---- both -----------------------------------------------------------------------------------------------------

@@ -283,6 +283,18 @@ struct CodeInRange {                            // column code (hot flag masked)
     }
 };
 
+// _TCSC_CF_ split of the (row', code) keys: 3 = source row, 2 = regular row x sink column, 0 = regular x regular
+struct CfPart {
+    uint32_t yreg, xchunk, xsnk0[kPullMaxSegs];      // first source-row position of the row segment; first sink position of every x chunk
+    int want;
+    __device__ int kind(const uint64_t& k) const {
+        if ((uint32_t) (k >> 32) >= yreg) return 3;
+        const uint32_t c = (uint32_t) k & ~kPullHotBit, q = c / xchunk;
+        return (c - q * xchunk) >= xsnk0[q] ? 2 : 0;
+    }
+    __device__ bool operator()(const uint64_t& k) const { return kind(k) == want; }
+};
+
 struct OwnPart {                                // entry belongs to the own-chunk part: code inside [lo, hi) and its row is split
     uint32_t lo, hi; const uint8_t* has_own; bool want;
     __device__ bool operator()(const uint64_t& k) const {
@@ -396,8 +408,18 @@ PullLayout* pull_build(gt_graph* g) {
 
     // concatenated x / y spaces (see PullLayout): chunk index = group rank of the segment's leader
     P->xoff.resize(S); P->xn.resize(S); P->yoff.resize(R); P->yn.resize(R);
-    for (size_t k = 0; k < S; k++) { P->xn[k] = g->hot[g->hot_of_col_slot[k]].n; P->xchunk = std::max(P->xchunk, P->xn[k]); }
-    for (size_t k = 0; k < R; k++) { P->yn[k] = g->hot[g->hot_of_row_slot[k]].n; P->ychunk = std::max(P->ychunk, P->yn[k]); }
+    P->xreg.resize(S); P->xsnk0.resize(S); P->yreg.resize(R); P->ysrc.resize(R);
+    P->cf = g->compression == GT_TCSC_CF;
+    for (size_t k = 0; k < S; k++) {
+        const HotOrder& H = g->hot[g->hot_of_col_slot[k]];
+        P->xn[k] = H.n; P->xchunk = std::max(P->xchunk, P->xn[k]);
+        P->xreg[k] = H.nreg; P->xsnk0[k] = P->cf ? H.nreg + H.nsrc : H.n;
+    }
+    for (size_t k = 0; k < R; k++) {
+        const HotOrder& H = g->hot[g->hot_of_row_slot[k]];
+        P->yn[k] = H.n; P->ychunk = std::max(P->ychunk, P->yn[k]);
+        P->yreg[k] = H.nreg; P->ysrc[k] = H.nsrc;
+    }
     P->xchunk = (P->xchunk + 1) / 2 * 2;       // keep every chunk 16-byte aligned
     P->ychunk = (P->ychunk + 1) / 2 * 2;
     for (size_t k = 0; k < S; k++) {
@@ -471,52 +493,87 @@ PullLayout* pull_build(gt_graph* g) {
             ctx->kernel_launches += 8;
             sorted = db.Current();
         }
-        // own x chunk apart from the rest (multi-GPU), or the hottest `band` columns apart from the tail (GT_PULL_BAND)
         uint64_t* other = (sorted == keys.p) ? alt.p : keys.p;
+        // _TCSC_CF_: [regular x regular | regular rows x sink columns | source rows], each still sorted by (row', code)
+        uint64_t n_rr = total, n_rs = 0, n_sx = 0;
+        if (P->cf) {
+            CfPart pred{};
+            pred.yreg = P->yreg[k]; pred.xchunk = P->xchunk;
+            for (uint32_t q = 0; q < kPullMaxSegs; q++) pred.xsnk0[q] = 0xffffffffu;
+            for (size_t c = 0; c < S; c++) pred.xsnk0[P->xoff[c] / P->xchunk] = P->xsnk0[c];
+            DevBuf<unsigned long long> d_n; d_n.alloc(1);
+            size_t tb = 0;
+            pred.want = 0;
+            GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) total, pred, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            uint64_t done = 0, cnt[3] = {0, 0, 0};
+            const int wants[3] = {0, 2, 3};
+            for (int w = 0; w < 3; w++) {
+                pred.want = wants[w];
+                unsigned long long h_n = 0;
+                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + done, d_n.p, (int64_t) total, pred, st));
+                GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+                GT_CUDA(cudaStreamSynchronize(st));
+                cnt[w] = h_n; done += h_n;
+            }
+            GT_REQUIRE(done == total, "pull layout: computation-filtering split lost entries");
+            n_rr = cnt[0]; n_rs = cnt[1]; n_sx = cnt[2];
+            ctx->kernel_launches += 3;
+            std::swap(sorted, other);
+        }
+        Q.nnz_rr = n_rr;
+        const uint64_t* cf_tail = sorted + n_rr;          // [RS | SX] stay here; the RR range may move to `other` below
+        // own x chunk apart from the rest (multi-GPU), or the hottest `band` columns apart from the tail (GT_PULL_BAND)
+        uint64_t* rr = sorted;
         uint64_t n_own = 0;
         const bool multi = ctx->comm && comm_size_in(ctx->comm, COMM_COLGRP) > 1;
         DevBuf<uint8_t> has_own;                               // GT_PULL_SPLIT_MIN: rows that get an own-chunk part
-        if (multi || P->band) {
+        if ((multi || P->band) && n_rr) {
             const uint32_t lo = multi ? P->xoff[g->lay.info.accu_segment_col] : 0, hi = multi ? lo + P->xchunk : P->band;
             DevBuf<unsigned long long> d_n; d_n.alloc(2);
             unsigned long long h_n = 0;
             if (P->split_min) {
                 DevBuf<uint64_t> rowptr; rowptr.alloc((size_t) nr + 1);
                 has_own.alloc(nr);
-                k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, total, nr, rowptr.p);
+                k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, n_rr, nr, rowptr.p);
                 k_rows_with_own_part<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(sorted, rowptr.p, nr, lo, hi, P->split_min, has_own.p);
                 ctx->kernel_launches += 2;
                 size_t tb = 0;
-                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) total, OwnPart{lo, hi, has_own.p, true}, st));
+                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, true}, st));
                 DevBuf<uint8_t> tmp; tmp.alloc(tb);
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) total, OwnPart{lo, hi, has_own.p, true}, st));
+                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, true}, st));
                 GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
                 GT_CUDA(cudaStreamSynchronize(st));
                 n_own = h_n;
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) total, OwnPart{lo, hi, has_own.p, false}, st));
+                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, false}, st));
                 GT_CUDA(cudaStreamSynchronize(st));
             } else {
                 size_t tb = 0;
-                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) total, CodeInRange{lo, hi, true}, st));
+                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
                 DevBuf<uint8_t> tmp; tmp.alloc(tb);
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) total, CodeInRange{lo, hi, true}, st));
+                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
                 GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
                 GT_CUDA(cudaStreamSynchronize(st));
                 n_own = h_n;
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) total, CodeInRange{lo, hi, false}, st));
+                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) n_rr, CodeInRange{lo, hi, false}, st));
                 GT_CUDA(cudaStreamSynchronize(st));
             }
             ctx->kernel_launches += 2;
-            sorted = other;
+            rr = other;
         }
-        if (n_own) build_sell(ctx, sorted, n_own, nr, vrow_for(n_own), pad_code, Q.own);
-        build_sell(ctx, sorted + n_own, total - n_own, nr, vrow_for(total - n_own), pad_code, Q.rest, P->split_min ? has_own.p : nullptr);
+        if (n_own) build_sell(ctx, rr, n_own, nr, vrow_for(n_own), pad_code, Q.own);
+        build_sell(ctx, rr + n_own, n_rr - n_own, nr, vrow_for(n_rr - n_own), pad_code, Q.rest, P->split_min ? has_own.p : nullptr);
+        if (n_rs) build_sell(ctx, cf_tail, n_rs, nr, vrow_for(n_rs), pad_code, Q.snk);
+        if (n_sx) build_sell(ctx, cf_tail + n_rs, n_sx, nr, vrow_for(n_sx), pad_code, Q.src);
         if (verbose)
             fprintf(stderr, "[gt pull] rank %d row slot %zu: rows %u entries %llu | part0 entries %llu (%.1f %%) vrows %u slices %u sell_len %llu (pad %.1f %%) | "
                             "part1 entries %llu vrows %u slices %u sell_len %llu (pad %.1f %%)\n", ctx->rank, k, nr, (unsigned long long) total,
                     (unsigned long long) Q.own.nnz, 100.0 * Q.own.nnz / total, Q.own.nv, Q.own.nslices, (unsigned long long) Q.own.sell_len,
                     Q.own.sell_len ? 100.0 * (Q.own.sell_len - Q.own.nnz) / Q.own.sell_len : 0.0, (unsigned long long) Q.rest.nnz, Q.rest.nv, Q.rest.nslices,
                     (unsigned long long) Q.rest.sell_len, Q.rest.sell_len ? 100.0 * (Q.rest.sell_len - Q.rest.nnz) / Q.rest.sell_len : 0.0);
+        if (verbose && P->cf)
+            fprintf(stderr, "[gt pull] rank %d row slot %zu: computation filtering: regular rows %u source rows %u | REG x REG %llu entries, REG x SNK %llu, SRC rows %llu\n",
+                    ctx->rank, k, P->yreg[k], P->ysrc[k], (unsigned long long) Q.nnz_rr, (unsigned long long) Q.snk.nnz, (unsigned long long) Q.src.nnz);
     }
     return P.release();
 }
@@ -527,8 +584,9 @@ void pull_free(PullLayout* P) { delete P; }
 // x = the concatenated, hot-ordered x buffer (x[xlen] == 0.0); y zero-filled by the caller
 void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, const double* x, double* y) {
     const PullRows& R = P->rows[row_slot];
-    const PullSell& Q = part == 0 ? R.own : R.rest;
-    const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : 0;
+    const PullSell& Q = part == 0 ? R.own : part == 1 ? R.rest : part == 2 ? R.snk : R.src;
+    // y is zero-filled before the pass: a plain store is right for the first part that can touch a row, += for the rest
+    const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : part == 2 ? 1 : 0;
     if (!Q.nslices) return;
     if (part == 0 && P->band_smem) {                  // hot band from shared memory: one CTA per SM, the whole carve-out
         const size_t smem = (size_t) P->band * sizeof(double);

@@ -25,6 +25,11 @@ struct PullRows {                               // one local row segment
     // Multi-GPU: entries whose column lies in this rank's OWN x chunk are kept apart, so that part of the SpMV can
     // run while the all-gather of the other chunks is still in flight.  Single GPU: `own` is empty.
     PullSell own, rest;
+    // _TCSC_CF_ graphs (computation filtering, src/vp/vertex_program.hpp:1218-1325): `own` / `rest` hold only the entries
+    // of REGULAR rows in REGULAR columns, which every iteration needs; `snk` = regular rows x sink columns (iteration 0
+    // only), `src` = source rows x every column (last iteration only).  Empty on _TCSC_ graphs.
+    PullSell snk, src;
+    uint64_t nnz_rr = 0;                        // entries of own + rest
 };
 
 struct PullLayout {
@@ -33,7 +38,10 @@ struct PullLayout {
     // src/vp/vertex_program.hpp:843-862).  Same for y and the row group with ncclReduceScatter.
     std::vector<uint32_t> xoff, xn;             // per column slot: chunk start, vertices in the segment's hot order
     uint32_t xchunk = 0, xlen = 0;              // chunk size, total; x[xlen] is a permanent 0.0 (padding target)
+    std::vector<uint32_t> xreg, xsnk0;          // per column slot: x positions [0, xreg) regular, [xsnk0, xn) sink columns (_TCSC_: xreg = xn)
     std::vector<uint32_t> yoff, yn;             // per row slot
+    std::vector<uint32_t> yreg, ysrc;           // per row slot: y positions [0, yreg) regular rows, [yreg, yreg + ysrc) source rows
+    bool cf = false;                            // the graph is _TCSC_CF_: rows / columns are split as above
     uint32_t ychunk = 0, ylen = 0;
     std::vector<PullRows> rows;                 // per row slot
     uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
@@ -51,7 +59,8 @@ struct PullLayout {
 
 PullLayout* pull_build(gt_graph* g);
 void pull_free(PullLayout* P);
-// part 0: the rank's own x chunk (y = ...), part 1: everything else (y += ... when part 0 exists)
+// part 0: the rank's own x chunk (y = ...), part 1: everything else (y += ... when part 0 exists),
+// part 2: regular rows x sink columns (y += ...), part 3: source rows (y = ...)
 void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, const double* x, double* y);
 
 }  // namespace gt

@@ -201,6 +201,24 @@ class Graph:
         d["_view"] = tv
         return d
 
+    def tile_cf(self, k: int) -> dict:
+        """TCSC_CF_BASE's four computation-filtering lists of local tile k (GT_TCSC_CF graphs)."""
+        cv = capi.TileCfView()
+        check(lib().gt_graph_tile_cf_view(self.handle, k, C.byref(cv)))
+        d = {}
+        for kind in range(4):
+            d[f"NC{kind}"], d[f"filled{kind}"] = cv.NC[kind], cv.filled[kind]
+            d[f"JA{kind}"] = self._download(cv.JA[kind], 2 * cv.NC[kind], "<u4")
+            d[f"JC{kind}"] = self._download(cv.JC[kind], cv.NC[kind], "<u4")
+        return d
+
+    def classify_lists(self):
+        """(regular_rows, source_rows, sink_columns) of the owned segment: local vertex ids (classify_vertices)."""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        ns = [C.c_uint32() for _ in range(3)]
+        check(lib().gt_graph_classify_lists(self.handle, C.byref(ptrs[0]), C.byref(ns[0]), C.byref(ptrs[1]), C.byref(ns[1]), C.byref(ptrs[2]), C.byref(ns[2])))
+        return tuple(self._download(p.value, n.value, "<u4") for p, n in zip(ptrs, ns))
+
     def rowgrp_maps(self, slot: int):
         I, IV, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
         check(lib().gt_graph_rowgrp_maps(self.handle, slot, C.byref(I), C.byref(IV), C.byref(n)))

@@ -178,10 +178,26 @@ GT_API int gt_graph_rowgrp_maps(gt_graph* g, uint32_t row_slot, const uint8_t** 
 GT_API int gt_graph_colgrp_maps(gt_graph* g, uint32_t col_slot, const uint8_t** J, const uint32_t** JV, uint32_t* nnzcols);
 
 /* classify_vertices on the owned segment (src/mat/matrix.hpp:1124-1144): regular = row and column non-empty, source
- * rows = row non-empty / column empty, sink columns = row empty / column non-empty.  These are the sets the
- * reference's _TCSC_CF_ "computation filtering" schedules by (src/vp/vertex_program.hpp:1218-1325); on the device
- * _TCSC_CF_ graphs run the _TCSC_ schedule, which gives bit-identical results in fixed-iteration mode. */
+ * rows = row non-empty / column empty, sink columns = row empty / column non-empty.  These are the sets the reference's
+ * _TCSC_CF_ "computation filtering" schedules by (src/vp/vertex_program.hpp:1218-1325,1671-1692,1902-1916); a graph built
+ * with GT_TCSC_CF runs that schedule on the device (gt_program_execute).  gt_graph_classify returns the counts (any
+ * compression), gt_graph_classify_lists the local vertex ids (rowgrp_regular_rows / rowgrp_source_rows /
+ * colgrp_sink_columns, :853-855; device pointers, GT_TCSC_CF graphs only). */
 GT_API int gt_graph_classify(gt_graph* g, uint32_t* regular, uint32_t* source_rows, uint32_t* sink_columns);
+GT_API int gt_graph_classify_lists(gt_graph* g, const uint32_t** regular_rows, uint32_t* nregular, const uint32_t** source_rows, uint32_t* nsource,
+                            const uint32_t** sink_columns, uint32_t* nsink);
+/* TCSC_CF_BASE (src/ds/compressed_column.hpp:419-1114) of one local tile of a GT_TCSC_CF graph: gt_graph_tile_view's IA
+ * (and A) are in the reference's order — every column's source-row entries moved behind its regular-row entries by
+ * the reference's own swap sequence (:671-708) — and the four computation-filtering lists, kind 0 = REG_R_REG_C,
+ * 1 = REG_R_SNK_C, 2 = SRC_R_REG_C, 3 = SRC_R_SNK_C: NC[k] (start, end) pairs into IA plus NC[k] compressed column ids.
+ * `filled[k]` pairs are written, the rest are zero: the reference sizes SRC_R_SNK_C by an EDGE count (:1046-1049) and
+ * starts its ranges at JA[j] + n (:1094); both quirks are reproduced so the arrays can be diffed. */
+typedef struct {
+    uint32_t NC[4], filled[4];
+    const uint32_t* JA[4];          /* [2 * NC[k]] */
+    const uint32_t* JC[4];          /* [NC[k]]     */
+} gt_tile_cf_view;
+GT_API int gt_graph_tile_cf_view(gt_graph* g, uint32_t local_tile, gt_tile_cf_view* out);
 
 /* ---- kernel level: replaces Vertex_Program::spmv_stationary / spmv_nonstationary -----------------
  * (src/vp/vertex_program.hpp:96-105,1115-1327,1437-1506).  x and y are device vectors in the tile's
@@ -225,6 +241,9 @@ typedef struct {
     uint64_t bytes_algorithmic;     /* SURVEY.md §8(d) algorithmic bytes moved inside execute()    */
     uint32_t iterations;
     uint32_t sparse_iterations;     /* iterations that ran the frontier SpMSpV                     */
+    uint64_t combine_bytes;         /* algorithmic bytes of the most recent combine phase (stationary programs): what the SpMV
+                                       pass of that iteration had to move; on a GT_TCSC_CF graph a middle iteration skips the
+                                       REG x SNK and source-row entries, as the reference does                                */
 } gt_timing;
 GT_API int gt_program_timing(gt_program* p, gt_timing* out);
 /* One phase of one iteration in isolation, for per-phase timing (the reference's -DTIMING counters,

@@ -10,6 +10,7 @@ EXE = os.path.join(ROOT, "apps", "gt_apps")
 G = os.path.join(ROOT, "tests", "golden")
 EXPECT = {  # Iterations / Value checksum / Reachable vertices
     "pr": ("rmat10_1024.bin", "20", (20, 70, 1025)),
+    "pr_until_converged": ("rmat10_1024.bin", None, (12, 51, 1025)),        # _TCSC_CF_ convergence mode, SURVEY.md §8c "quirky path"
     "bfs": ("rmat10_1024.bin", "0", (4, 1912, 887)),
     "cc": ("rmat10_1024.bin", None, (4, 69590, 1025)),
     "sssp": ("rmat10_1024_w.bin", "0", (7, 53366, 471)),
@@ -24,7 +25,7 @@ def test_shim_compiles_against_the_c_abi():
 @pytest.mark.parametrize("app", sorted(EXPECT))
 def test_cpp_driver_prints_reference_checksums(app):
     f, arg, (it, cs, reach) = EXPECT[app]
-    cmd = [EXE, app, os.path.join(G, f), "1024"] + ([arg] if arg else [])
+    cmd = [EXE, app.split("_")[0], os.path.join(G, f), "1024"] + ([arg] if arg else [])
     out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout
     get = lambda k: int([l for l in out.splitlines() if l.startswith(k)][-1].split()[-1])
     assert (get("Iterations:"), get("Value checksum:"), get("Reachable vertices:")) == (it, cs, reach)

@@ -473,3 +473,72 @@ def test_bfs_bottom_up_equals_top_down(scale, seed):
             assert (mine[f][: n + 1] == ref[f][: n + 1]).all(), (ratio, f)
         V.free()
     G.free()
+
+
+# ---- _TCSC_CF_: computation filtering ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["fixture", "rmat12"])
+def test_cf_lists_and_classes_match_reference(which, fixture_unweighted, rmat12, golden_fixture, golden_rmat12):
+    """TCSC_CF_BASE::populate on the device: IA in the reference's order after its source-row swap, the four
+    (start,end)-pair lists with their column lists — quirks included — and classify_vertices' id lists, against the
+    dumps of the unmodified reference and against the CPU oracle."""
+    E, O = _E(), _O()
+    tri, n, gold = (fixture_unweighted, 1024, golden_fixture) if which == "fixture" else (rmat12[:, :2].copy(), 4096, golden_rmat12)
+    G = E.Graph(weighted=False)
+    G.load_triples(tri, n, directed=True, transpose=True, self_loops=True, parallel_edges=True, compression_type=E._TCSC_CF_)
+    t, cf = G.tile(0), G.tile_cf(0)
+    base = "pr_np1_tile_r0.t0"
+    np.testing.assert_array_equal(t["JA"], gold[base + "_JA"])
+    np.testing.assert_array_equal(t["IA"], gold[base + "_IA"])
+    assert [cf[f"NC{k}"] for k in range(4)] == list(gold[base + "_cfnc"])
+    for k in range(4):
+        np.testing.assert_array_equal(cf[f"JA{k}"], gold[base + f"_cf{k}.JA"])
+        np.testing.assert_array_equal(cf[f"JC{k}"], gold[base + f"_cf{k}.JC"])
+    reg, src, snk = G.classify_lists()
+    np.testing.assert_array_equal(reg, gold["pr_np1_regrows_r0"])
+    np.testing.assert_array_equal(src, gold["pr_np1_srcrows_r0"])
+    np.testing.assert_array_equal(snk, gold["pr_np1_snkcols_r0"])
+    fl = dict(O.APP_FLAGS["pr"]); fl.pop("weighted")
+    og = O.OracleGraph(tri, n, 1, weighted=0, **fl)
+    ot = og.cf_tile(0, 0)
+    assert [cf[f"filled{k}"] for k in range(4)] == [ot[f"filled{k}"] for k in range(4)]
+    og.close(); G.free()
+
+
+@pytest.mark.parametrize("layout", [1, 0])
+@pytest.mark.parametrize("which", ["fixture", "rmat12"])
+def test_pagerank_convergence_mode(which, layout, fixture_unweighted, rmat12, golden_fixture, golden_rmat12):
+    """`pr <file> <n>` without an iteration count.  _TCSC_CF_ (pr.cpp): has_converged() looks at the regular rows only and
+    the source rows end at alpha (fixture: 12 iterations, checksum 51); _TCSC_ (pr1.cpp): the plain loop (13 / 70)."""
+    E = _E()
+    tri, n, gold = (fixture_unweighted, 1024, golden_fixture) if which == "fixture" else (rmat12[:, :2].copy(), 4096, golden_rmat12)
+    for comp, key in ((E._TCSC_CF_, "prconv"), (E._TCSC_, "pr1conv")):
+        G, P = E.run_pr(loader(tri, n), 0, compression=comp, pr_layout=layout)
+        mine, it, cs = P.V, P.iteration, P.checksum(quiet=True)
+        P.free(); G.free()
+        meta = gold[f"{key}_np1_meta"]
+        assert it == meta[0], (key, it)
+        assert_states("pr", mine, gold[f"{key}_np1_V"], n + 1)
+        if layout == 0:                                 # the push path keeps the reference's vertex order in the checksum loop
+            assert cs[1] == meta[2]
+    if which == "fixture":
+        G, P = E.run_pr(loader(tri, n), 0, compression=E._TCSC_CF_, pr_layout=layout)
+        assert (P.iteration, P.checksum(quiet=True)) == (12, (51, 1025))
+        P.free(); G.free()
+
+
+def test_pagerank_cf_schedule_at_scale_20():
+    """Fixed-iteration PageRank on a _TCSC_CF_ graph (REG x REG every iteration, REG x SNK first, source rows last) against the
+    same run on a _TCSC_ graph, per vertex, plus the 1-iteration and 2-iteration corner cases of the schedule."""
+    from graphtap_b200.rmat import rmat_edges
+    E = _E()
+    tri = rmat_edges(20, nedges=8 << 20, seed=5)
+    n = 1 << 20
+    for iters in (1, 2, 20):
+        out = {}
+        for comp in (E._TCSC_, E._TCSC_CF_):
+            G, P = E.run_pr(loader(tri, n), iters, compression=comp)
+            out[comp] = P.V
+            P.free(); G.free()
+        assert (out[E._TCSC_]["degree"] == out[E._TCSC_CF_]["degree"]).all()
+        rel = np.abs(out[E._TCSC_]["rank"] - out[E._TCSC_CF_]["rank"]) / out[E._TCSC_]["rank"]
+        assert rel.max() <= 1e-12, (iters, rel.max())
