@@ -444,6 +444,33 @@ static void pull_state_out(gt_program* P) {
 //  * every put is consumed (its counter waited for) before execute() / run_phase() returns, so a window is never
 //    written after its owner could have freed it.
 // x buffer the current iteration reads (parity of the last put) / the one the next messenger writes
+static void tl_mark(gt_program* P, const char* tag, cudaStream_t s) {
+    if (!P->timeline_on) return;
+    cudaEvent_t ev;
+    if (!P->timeline_pool.empty()) { ev = P->timeline_pool.back(); P->timeline_pool.pop_back(); }
+    else GT_CUDA(cudaEventCreate(&ev));
+    GT_CUDA(cudaEventRecord(ev, s));
+    P->timeline.push_back({ev, tag, P->iteration});
+}
+static void tl_dump(gt_program* P) {
+    if (!P->timeline_on) return;
+    const char* prefix = getenv("GT_TIMELINE");
+    std::string path = std::string(prefix ? prefix : "gt_timeline") + ".r" + std::to_string(P->ctx->rank) + ".jsonl";
+    FILE* f = fopen(path.c_str(), "a");
+    if (f) fprintf(f, "{\"rank\": %d, \"marks\": [", P->ctx->rank);
+    bool firstm = true;
+    for (const gt_program::Mark& m : P->timeline) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, P->ev0, m.ev) == cudaSuccess && f) {
+            fprintf(f, "%s[%u, \"%s\", %.4f]", firstm ? "" : ", ", m.iteration, m.tag, ms);
+            firstm = false;
+        }
+        P->timeline_pool.push_back(m.ev);
+    }
+    cudaGetLastError();
+    if (f) { fprintf(f, "]}\n"); fclose(f); }
+    P->timeline.clear();
+}
 static inline double* pull_x_cur(gt_program* P) { return P->xbuf[P->wx ? (P->x_epoch & 1) : 0]; }
 static inline double* pull_x_next(gt_program* P) { return P->xbuf[P->wx ? ((P->x_epoch + 1) & 1) : 0]; }
 
@@ -483,6 +510,7 @@ static void pull_scatter_gather(gt_program* P) {
             peer_put(ctx, P->wx, q, off, xo, (size_t) nput * sizeof(double), P->x_epoch);
         }
         peer_put_end(ctx, nullptr);
+        for (int j = 0; j < std::min(ctx->peer_lanes, P->wx->size - 1); j++) tl_mark(P, "x_put_done", ctx->put_stream[j]);
         P->x_wait_pending = true;
     } else if (ctx->comm && comm_size_in(ctx->comm, P->bcast_group) > 1) {      // every member leads exactly one of the group's segments
         // the all-gather runs on its own stream; the SpMV over the own chunk does not wait for it
@@ -525,8 +553,11 @@ static void pull_combine(gt_program* P) {
     // Part 0 needs only this rank's own x chunk, so it runs while the other chunks are still arriving.
     for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) pull_spmv(ctx, L, (uint32_t) k, 0, x, P->Yh.p + L->yoff[k]);
     if (L->yn[own]) pull_spmv(ctx, L, (uint32_t) own, 0, x, P->Yh.p + L->yoff[own]);
+    tl_mark(P, "own_parts_done", st);
     pull_x_arrived(P);
+    tl_mark(P, "x_arrived", st);
     for (size_t k = 0; k < R; k++) if (k != own && L->yn[k]) remote_parts(k);
+    tl_mark(P, "follower_rows_done", st);
     if (P->wy) {
         // combine_2d_stationary's follower -> leader sends (:1083-1108) as puts into slot `me` of the leader's window;
         // with computation filtering only the rows the leader will apply: the regular ones, plus the source rows at the end
@@ -542,10 +573,12 @@ static void pull_combine(gt_program* P) {
             peer_put(ctx, P->wy, q, off, P->Yh.p + L->yoff[k], (size_t) ny * sizeof(double), P->y_epoch);
         }
         peer_put_end(ctx, P->ev_yput);
+        tl_mark(P, "y_put_done", ctx->put_stream[0]);
         P->ypush_pending = true;
     }
     if (L->yn[own]) remote_parts(own);
-    if (P->wy) peer_wait_all(ctx, P->wy, P->y_epoch, st);                       // the followers' partials of the owned segment
+    tl_mark(P, "own_rows_done", st);
+    if (P->wy) { peer_wait_all(ctx, P->wy, P->y_epoch, st); tl_mark(P, "y_arrived", st); }     // the followers' partials of the owned segment
     else if (ctx->comm && comm_size_in(ctx->comm, P->reduce_group) > 1)
         comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, P->Yh.p, L->ychunk, CT_F64, CO_SUM, st);
 }
@@ -676,6 +709,7 @@ extern "C" int gt_program_free(gt_program* p) {
         if (!p) return;
         cudaSetDevice(p->ctx->device);
         gt::ns_free(p);
+        for (cudaEvent_t e : p->timeline_pool) cudaEventDestroy(e);
         if (p->h_active) cudaFreeHost(p->h_active);
         if (p->ev0) cudaEventDestroy(p->ev0);
         if (p->ev1) cudaEventDestroy(p->ev1);
@@ -749,11 +783,13 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
                 GT_CUDA(cudaStreamSynchronize(ctx->stream));
                 acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             };
+            p->timeline_on = p->pull && getenv("GT_TIMELINE") != nullptr;
             while (true) {
                 phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
                 phase(p->tm.combine_ms, [&] { gt::combine(p); });
                 p->tm.bytes_algorithmic += gt::algorithmic_bytes_iteration(p, gt::cf_first(p), gt::cf_last(p), false);
                 phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
+                gt::tl_mark(p, "applied", ctx->stream);
                 p->iteration++;
                 if (check) {
                     gt::has_converged_begin(p);
@@ -787,6 +823,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         float ms = 0;
         GT_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
         p->tm.execute_ms = ms;
+        if (p->timeline_on) { for (int i = 0; i < GT_PEER_MAX_LANES; i++) if (ctx->put_stream[i]) cudaStreamSynchronize(ctx->put_stream[i]); gt::tl_dump(p); }
         p->tm.kernel_launches = ctx->kernel_launches - launches0;
         p->tm.iterations = p->iteration - it0;
         if (iters_done) *iters_done = p->iteration;

@@ -78,6 +78,12 @@ struct gt_program {
     bool in_execute = false, check_mode = false;
     uint32_t num_iterations = 0;
     uint64_t combine_bytes = 0;                    // algorithmic bytes of the most recent combine phase
+    // GT_TIMELINE=<path prefix>: CUDA events at the phase boundaries of every iteration of the pull path, on the main
+    // stream and on the put streams, written as one JSON line per execute() and rank (there is no nsys in the image)
+    struct Mark { cudaEvent_t ev; const char* tag; uint32_t iteration; };
+    std::vector<Mark> timeline;
+    std::vector<cudaEvent_t> timeline_pool;
+    bool timeline_on = false;
     // ---- non-stationary programs (gt_ns.cu) ------------------------------------------------------------------
     gt::NsState* ns = nullptr;
     // ---- both -----------------------------------------------------------------------------------------------------

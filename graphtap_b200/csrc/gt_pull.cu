@@ -585,8 +585,10 @@ void pull_free(PullLayout* P) { delete P; }
 void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, const double* x, double* y) {
     const PullRows& R = P->rows[row_slot];
     const PullSell& Q = part == 0 ? R.own : part == 1 ? R.rest : part == 2 ? R.snk : R.src;
-    // y is zero-filled before the pass: a plain store is right for the first part that can touch a row, += for the rest
-    const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : part == 2 ? 1 : 0;
+    // y is zero-filled before the pass.  Only the first part launched may use the plain store: every SELL array carries a
+    // (possibly empty) virtual row for EVERY row of the segment, so a later part that stored instead of adding would wipe
+    // the rows that merely share its last slice — the hottest ones, which sort first among the empty rows.
+    const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : part >= 2 ? 1 : 0;
     if (!Q.nslices) return;
     if (part == 0 && P->band_smem) {                  // hot band from shared memory: one CTA per SM, the whole carve-out
         const size_t smem = (size_t) P->band * sizeof(double);
