@@ -106,7 +106,8 @@ struct IngestParams {
     const int32_t* tile_local;       // [p*p] local tile index (row order) or -1
     uint8_t* I_all;                  // [p*th] any entry in this row    (count pass only)
     uint8_t* J_all;                  // [p*th] any entry in this column (count pass only)
-    uint32_t* deg_all;               // [p*th] entries in the vertex's row + column (count pass only)
+    uint32_t* rdeg_all;              // [p*th] entries in the vertex's row    (count pass only; raw records, before dedup)
+    uint32_t* cdeg_all;              // [p*th] entries in the vertex's column (count pass only)
     unsigned long long* counters;    // [0] owned entries, [1] append cursor, [2] out-of-range records
     uint64_t* keys;                  // fill pass
     uint32_t* wts;                   // fill pass, weighted
@@ -121,7 +122,7 @@ __device__ __forceinline__ void ingest_emit(const IngestParams& Q, uint32_t r, u
         rg = r / Q.th;
         cg = c / Q.th;
         t = Q.tile_local[rg * Q.p + cg];
-        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.deg_all + r, 1u); atomicAdd(Q.deg_all + c, 1u); }
+        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.rdeg_all + r, 1u); atomicAdd(Q.cdeg_all + c, 1u); }
     }
     const bool own = valid && t >= 0;
     if (!FILL) {
@@ -196,12 +197,12 @@ __global__ void k_seg_maps(const uint8_t* bits_all, const uint32_t* scan_all, ui
 
 // hot order: key = (class, ~degree, local id) for vertices with a non-empty row or column, all-ones otherwise.
 // class (only on _TCSC_CF_ graphs, else 0 for everyone): 0 regular, 1 source row, 2 sink column.
-__global__ void k_hot_keys(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, const uint32_t* __restrict__ deg, uint32_t th, int cf,
+__global__ void k_hot_keys(const uint8_t* __restrict__ I, const uint8_t* __restrict__ J, const uint32_t* __restrict__ rdeg, const uint32_t* __restrict__ cdeg, uint32_t th, int cf,
                            uint64_t* __restrict__ keys, uint8_t* __restrict__ cls, unsigned int* __restrict__ counts) {
     unsigned int nreg = 0, nsrc = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < th; i += gridDim.x * blockDim.x) {
         const bool r = I[i], c = J[i];
-        const uint32_t d = min(deg[i], 0x3fffffffu);
+        const uint32_t d = (uint32_t) min((uint64_t) rdeg[i] + cdeg[i], (uint64_t) 0x3fffffffu);
         const uint64_t k = (cf && !(r && c)) ? (r ? 1ull : 2ull) : 0ull;
         keys[i] = (r || c) ? ((k << 62) | ((uint64_t) (0x3fffffffu - d) << 32) | i) : ~0ull;
         if (cls) cls[i] = (uint8_t) (r && c ? 1 : r ? 2 : c ? 3 : 0);       // matrix.hpp:1135-1144
@@ -299,6 +300,7 @@ __global__ void k_cf_flags(const uint32_t* __restrict__ IA, uint64_t nnz, const 
         F[e] = e < nnz ? (rcls[IR[IA[e]]] == 2) : 0;
 }
 struct U8ToU32 { __host__ __device__ uint32_t operator()(const uint8_t& v) const { return v; } };
+struct U32ToU64 { __host__ __device__ unsigned long long operator()(const uint32_t& v) const { return v; } };
 __device__ __forceinline__ uint32_t cf_col_of(const uint32_t* __restrict__ JA, uint32_t ncols, uint64_t e) {
     uint32_t lo = 0, hi = ncols;                      // upper_bound(JA, e) - 1 = the column that holds entry e
     while (lo < hi) {
@@ -501,8 +503,10 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     I_all.alloc(nall); J_all.alloc(nall);
     GT_CUDA(cudaMemsetAsync(I_all.p, 0, nall, st));
     GT_CUDA(cudaMemsetAsync(J_all.p, 0, nall, st));
-    DevBuf<uint32_t> deg_all; deg_all.alloc(nall);
-    GT_CUDA(cudaMemsetAsync(deg_all.p, 0, nall * 4, st));
+    DevBuf<uint32_t> rdeg_all, cdeg_all;
+    rdeg_all.alloc(nall); cdeg_all.alloc(nall);
+    GT_CUDA(cudaMemsetAsync(rdeg_all.p, 0, nall * 4, st));
+    GT_CUDA(cudaMemsetAsync(cdeg_all.p, 0, nall * 4, st));
     DevBuf<unsigned long long> counters; counters.alloc(4);
     GT_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), st));
 
@@ -510,7 +514,7 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     Q.th = th; Q.p = p;
     Q.self_loops = flags->self_loops; Q.acyclic = flags->acyclic; Q.transpose = flags->transpose; Q.directed = flags->directed;
     Q.weighted = weighted; Q.bw = bw;
-    Q.tile_local = d_tile_local.p; Q.I_all = I_all.p; Q.J_all = J_all.p; Q.deg_all = deg_all.p; Q.counters = counters.p;
+    Q.tile_local = d_tile_local.p; Q.I_all = I_all.p; Q.J_all = J_all.p; Q.rdeg_all = rdeg_all.p; Q.cdeg_all = cdeg_all.p; Q.counters = counters.p;
     RmatParams G{};
     if (gen) G = *gen;
 
@@ -667,7 +671,7 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
             const uint64_t b = (uint64_t) segs[h] * th;
             if (cf) g->cls[h].alloc(th);
             GT_CUDA(cudaMemsetAsync(d_n.p, 0, 12, st));
-            k_hot_keys<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(I_all.p + b, J_all.p + b, deg_all.p + b, th, cf, keys.p, cf ? g->cls[h].p : nullptr, d_n.p + 1);
+            k_hot_keys<<<grid_for(th, 256, ctx->sm_count), 256, 0, st>>>(I_all.p + b, J_all.p + b, rdeg_all.p + b, cdeg_all.p + b, th, cf, keys.p, cf ? g->cls[h].p : nullptr, d_n.p + 1);
             cub::DoubleBuffer<uint64_t> db(keys.p, alt.p);
             GT_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tb, db, (int64_t) th, 0, 64, st));
             k_hot_count<<<1, 1, 0, st>>>(db.Current(), th, d_n.p);
@@ -688,7 +692,30 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
         for (int32_t r : L.local_row_segments) g->hot_of_row_slot.push_back(find_hot(r));
         for (int32_t c : L.local_col_segments) g->hot_of_col_slot.push_back(find_hot(c));
     }
-    I_all.release(); J_all.release(); deg_all.release();
+    // column degrees of the local column segments (raw record counts over the WHOLE matrix): the non-stationary engine
+    // sizes a frontier by its edges, not only by its columns
+    g->col_deg.resize(L.local_col_segments.size());
+    g->col_edges.assign(L.local_col_segments.size(), 0);
+    {
+        DevBuf<unsigned long long> d_sum; d_sum.alloc(1);
+        DevBuf<uint8_t> tmp;
+        size_t tb = 0;
+        GT_CUDA(cub::DeviceReduce::Sum(nullptr, tb, cdeg_all.p, d_sum.p, (int) th, st));
+        tmp.alloc(tb);
+        for (size_t k = 0; k < L.local_col_segments.size(); k++) {
+            const uint64_t b = (uint64_t) L.local_col_segments[k] * th;
+            g->col_deg[k].alloc(th);
+            GT_CUDA(cudaMemcpyAsync(g->col_deg[k].p, cdeg_all.p + b, (size_t) th * 4, cudaMemcpyDeviceToDevice, st));
+            cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> in(cdeg_all.p + b, U32ToU64());
+            GT_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, in, d_sum.p, (int) th, st));
+            unsigned long long h = 0;
+            GT_CUDA(cudaMemcpyAsync(&h, d_sum.p, 8, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            g->col_edges[k] = h;
+        }
+        ctx->kernel_launches += L.local_col_segments.size();
+    }
+    I_all.release(); J_all.release(); rdeg_all.release(); cdeg_all.release();
 
     // ---- tiles ------------------------------------------------------------------------------------
     std::vector<uint64_t> bounds(ntiles + 1, 0);

@@ -732,6 +732,7 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         else if (n == "iteration") { p->iteration = (uint32_t) value; p->converged = false; }   // public member, vertex_program.hpp:60
         else if (n == "pr_layout") { p->pr_layout = (int) value; p->initialized = false; }
         else if (n == "bfs_bottom_up_ratio") p->bfs_bottom_up_ratio = value;
+        else if (n == "dense_edge_ratio") p->dense_edge_ratio = value;
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
 }

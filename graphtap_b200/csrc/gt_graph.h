@@ -68,6 +68,8 @@ struct gt_graph {
     gt::DevBuf<uint32_t> IA_pool, A_pool;    // concatenated per-tile IA / A
     gt::DevBuf<uint2> heavy_list;            // frontier SpMSpV scratch: (frontier position, chunk) of heavy columns + a counter
     gt::DevBuf<unsigned int> heavy_count;
+    std::vector<gt::DevBuf<uint32_t>> col_deg;   // per local column slot: entries in the vertex's column over the whole matrix (raw records)
+    std::vector<uint64_t> col_edges;         // their sum
     std::vector<gt::CfTile> cf_tiles;        // _TCSC_CF_ only, parallel to `tiles`
     gt::CfOwned cf_owned;                    // _TCSC_CF_ only
     std::vector<gt::DevBuf<uint8_t>> cls;    // _TCSC_CF_ only, per distinct local segment (same index as `hot`): 1 regular, 2 source row, 3 sink column

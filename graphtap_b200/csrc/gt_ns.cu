@@ -79,7 +79,8 @@ struct NsState {
     DevBuf<uint2> heavy_list;
     DevBuf<unsigned int> slot_counts;            // NCCL exchange only: frontier size of every x slot
     DevBuf<unsigned int> counters;               // [0] heavy count, [1] own frontier count, [2] x put done, [3 + 2 i] y count i, [4 + 2 i] y put done i
-    DevBuf<unsigned long long> stats;            // [0] algorithmic bytes of the tile passes, [1] iterations with a sparse tile, [2] flag of the running one
+    DevBuf<unsigned long long> stats;            // [0] algorithmic bytes of the tile passes, [1] iterations with a sparse tile, [2] flag of the running one,
+                                                 // [3] size in edges of the frontier being built
     uint32_t x_epoch = 0, y_epoch = 0;
     bool any_heavy = false, bottom_up_ok = false, nccl_exchange = false;
     cudaEvent_t ev_it[2] = {nullptr, nullptr};
@@ -88,13 +89,19 @@ struct NsState {
 
 // ---- scatter_gather from the vertex state (first iteration of an execute(), run_phase(0)) ----------------------------------
 // non-stationary messenger: x[j] = C[v] ? messenger(V[v]) : infinity() (:737-751)
-__global__ void k_ns_messenger(VState V, int app, uint32_t vid0, const uint32_t* __restrict__ JC, uint32_t nc, uint32_t* __restrict__ x) {
+// also sums the column degrees of the active vertices (the frontier's size in edges, see ns_mode)
+__global__ void k_ns_messenger(VState V, int app, uint32_t vid0, const uint32_t* __restrict__ JC, uint32_t nc, uint32_t* __restrict__ x,
+                               const uint32_t* __restrict__ cdeg, unsigned long long* __restrict__ frontier_edges) {
+    unsigned long long fe = 0;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nc; j += gridDim.x * blockDim.x) {
         const uint32_t v = JC[j];
         uint32_t m = GT_INF_U32;
-        if (V.C[v]) m = (app == GT_APP_BFS) ? vid0 + v : V.a[v];                            // bfs.h:52-54, cc.h:37-39, sssp.h:45-47
+        if (V.C[v]) { m = (app == GT_APP_BFS) ? vid0 + v : V.a[v]; fe += cdeg[v]; }         // bfs.h:52-54, cc.h:37-39, sssp.h:45-47
         x[j] = m;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fe += __shfl_xor_sync(0xffffffffu, fe, o);
+    if ((threadIdx.x & 31) == 0 && fe) atomicAdd(frontier_edges, fe);
 }
 // frontier list of one x segment: xi = compressed ids with x != INF, xv = their values (:744-748); order inside
 // the list is irrelevant to a min reduction.  One atomic per CTA per 4096 elements (block scan of the per-thread counts).
@@ -139,16 +146,23 @@ __device__ __forceinline__ void copy_u32(uint32_t* __restrict__ dst, const uint3
     for (uint32_t i = tid; i < n4; i += nth) d4[i] = s4[i];
     for (uint32_t i = (n4 << 2) + tid; i < n; i += nth) dst[i] = src[i];
 }
-__device__ __forceinline__ uint32_t ns_mode(unsigned k, uint32_t n, double ratio, double bu_ratio) {
-    uint32_t mode = (n && ((double) k / (double) n <= ratio)) ? NS_SPARSE : NS_DENSE;        // :768-772
-    if (bu_ratio > 0.0 && (double) k > bu_ratio * (double) n) mode = NS_BOTTOM_UP;
+// The reference's rule is by columns: sparse when at most `ratio` (0.6) of the segment's columns are active (:768-772).
+// On RMAT that calls "sparse" a frontier of a third of the columns that holds three quarters of the edges, for which the
+// frontier kernel (one RED per edge into random rows) takes twice as long as the dense pass — so the owner also sizes
+// the frontier in EDGES (sum of the active columns' degrees) and goes dense above `edge_ratio` of the segment's edges.
+// The choice changes which kernel runs and what travels, never the result.
+struct NsRule { double ratio, bu_ratio, edge_ratio; unsigned long long seg_edges; };
+__device__ __forceinline__ uint32_t ns_mode(unsigned k, uint32_t n, unsigned long long fe, const NsRule& R) {
+    uint32_t mode = (n && ((double) k / (double) n <= R.ratio)) ? NS_SPARSE : NS_DENSE;
+    if (mode == NS_SPARSE && R.edge_ratio > 0.0 && (double) fe > R.edge_ratio * (double) R.seg_edges) mode = NS_DENSE;
+    if (R.bu_ratio > 0.0 && (double) k > R.bu_ratio * (double) n) mode = NS_BOTTOM_UP;
     return mode;
 }
 __global__ void __launch_bounds__(256) k_ns_put_x(const uint32_t* __restrict__ dense, const uint32_t* __restrict__ xi, const uint32_t* __restrict__ xv,
-                                                   const unsigned int* __restrict__ count, uint32_t n, double ratio, double bu_ratio, uint32_t* own_hdr,
-                                                   PutTargets T, uint32_t epoch, unsigned int* done) {
+                                                   const unsigned int* __restrict__ count, uint32_t n, const unsigned long long* __restrict__ frontier_edges,
+                                                   NsRule rule, uint32_t* own_hdr, PutTargets T, uint32_t epoch, unsigned int* done) {
     const unsigned k = *count;
-    const uint32_t mode = ns_mode(k, n, ratio, bu_ratio);
+    const uint32_t mode = ns_mode(k, n, *frontier_edges, rule);
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int j = 0; j < T.n; j++) {
         if (mode == NS_SPARSE) { copy_u32(T.xi[j], xi, k, tid, nth); copy_u32(T.xv[j], xv, k, tid, nth); }
@@ -171,9 +185,9 @@ __global__ void __launch_bounds__(256) k_ns_put_x(const uint32_t* __restrict__ d
     }
 }
 // NCCL fallback (GT_PEER=0): dense x arrived by all-gather, every rank rebuilds the lists and applies the rule itself
-__global__ void k_ns_header(const unsigned int* __restrict__ count, uint32_t n, double ratio, double bu_ratio, uint32_t* hdr) {
+__global__ void k_ns_header(const unsigned int* __restrict__ count, uint32_t n, NsRule rule, uint32_t* hdr) {
     const unsigned k = *count;
-    hdr[0] = ns_mode(k, n, ratio, bu_ratio); hdr[1] = k;
+    hdr[0] = ns_mode(k, n, 0ull, rule); hdr[1] = k;
 }
 
 // ---- combine: the tile passes ----------------------------------------------------------------------------------------------
@@ -368,13 +382,15 @@ __global__ void __launch_bounds__(256) k_ns_merge_y(const NsYRecv* __restrict__ 
 // compaction: a vertex is active next iteration iff its applicator returned true now.
 __global__ void __launch_bounds__(256)
 k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __restrict__ IR, uint32_t nr, const uint32_t* __restrict__ y, uint32_t iteration,
-           const uint8_t* __restrict__ J, const uint32_t* __restrict__ JV, uint32_t* __restrict__ x, uint32_t* __restrict__ xi, uint32_t* __restrict__ xv,
-           unsigned int* __restrict__ count, unsigned long long* __restrict__ active, unsigned long long* __restrict__ stats) {
+           const uint8_t* __restrict__ J, const uint32_t* __restrict__ JV, const uint32_t* __restrict__ cdeg, uint32_t* __restrict__ x,
+           uint32_t* __restrict__ xi, uint32_t* __restrict__ xv, unsigned int* __restrict__ count, unsigned long long* __restrict__ active,
+           unsigned long long* __restrict__ stats) {
     typedef cub::BlockScan<unsigned, 256> BS;
     __shared__ typename BS::TempStorage tmp;
     __shared__ unsigned base_s;
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats[2]) { stats[1]++; stats[2] = 0; }
     unsigned changed = 0;
+    unsigned long long fe = 0;                                         // the next frontier's size in edges -> stats[3]
     const uint32_t per_iter = 256 * 4;
     for (uint32_t start = blockIdx.x * per_iter; start < nr; start += gridDim.x * per_iter) {
         uint32_t cj[4], cm[4];
@@ -406,7 +422,7 @@ k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __res
             if (J[v]) {                                                // the vertex has a column: next iteration's x (:737-751)
                 const uint32_t j = JV[v];
                 x[j] = ch ? msg : GT_INF_U32;
-                if (ch) { cj[u] = j; cm[u] = msg; mine++; }
+                if (ch) { cj[u] = j; cm[u] = msg; mine++; fe += cdeg[v]; }
             }
         }
         unsigned off, total;
@@ -425,6 +441,9 @@ k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __res
     __shared__ typename BR::TempStorage tmp2;
     const unsigned tot = BR(tmp2).Sum(changed);
     if (threadIdx.x == 0 && tot) atomicAdd(active, (unsigned long long) tot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fe += __shfl_xor_sync(0xffffffffu, fe, o);
+    if ((threadIdx.x & 31) == 0 && fe) atomicAdd(stats + 3, fe);
 }
 // After the first applicator pass: vertices whose row is empty everywhere take applicator(state) -> false (:1726-1738,
 // :38), so they are never active again and their x stays infinity() from now on.
@@ -582,8 +601,9 @@ static void ns_x_from_state(gt_program* P) {
     const SegMaps& own = (*P->pcol)[P->own_col_slot];
     const int k = P->own_col_slot;
     GT_CUDA(cudaMemsetAsync(N.counters.p + 1, 0, sizeof(unsigned int), st));
+    GT_CUDA(cudaMemsetAsync(N.stats.p + 3, 0, sizeof(unsigned long long), st));
     if (own.nnz) {
-        k_ns_messenger<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, N.x[k]);
+        k_ns_messenger<<<grid_for(own.nnz, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->vid0, own.ids.p, own.nnz, N.x[k], P->g->col_deg[k].p, N.stats.p + 3);
         k_ns_frontier<<<grid_for((own.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>(N.x[k], own.nnz, N.xi[k], N.xv[k], N.counters.p + 1);
         ctx->kernel_launches += 2;
     }
@@ -598,6 +618,7 @@ static void ns_exchange_x(gt_program* P) {
     const SegMaps& own = (*P->pcol)[P->own_col_slot];
     const int k = P->own_col_slot;
     const double bu = N.bottom_up_ok ? P->bfs_bottom_up_ratio : 0.0;
+    const NsRule rule{P->activity_filtering_ratio, bu, P->activity_filtering_ratio >= 1.0 ? 0.0 : P->dense_edge_ratio, P->g->col_edges[k]};
     uint32_t* own_hdr = N.hdr + 4 * (size_t) N.xq[k];
     if (N.nccl_exchange) {
         // GT_PEER=0 or no peer mapping: ONE in-place all-gather of the dense segments; every rank rebuilds the lists of
@@ -611,7 +632,7 @@ static void ns_exchange_x(gt_program* P) {
                 k_ns_frontier<<<grid_for((seg.nnz + 3) / 4, 1024, ctx->sm_count, 2), 1024, 0, st>>>(N.x[s], seg.nnz, N.xi[s], N.xv[s], cnt);
                 ctx->kernel_launches++;
             }
-            k_ns_header<<<1, 1, 0, st>>>(cnt, seg.nnz, P->activity_filtering_ratio, (int) s == k ? bu : 0.0, N.hdr + 4 * (size_t) N.xq[s]);
+            k_ns_header<<<1, 1, 0, st>>>(cnt, seg.nnz, NsRule{P->activity_filtering_ratio, (int) s == k ? bu : 0.0, 0.0, 0ull}, N.hdr + 4 * (size_t) N.xq[s]);
             ctx->kernel_launches++;
         }
         GT_CUDA(cudaGetLastError());
@@ -632,7 +653,7 @@ static void ns_exchange_x(gt_program* P) {
         }
     }
     N.x_epoch++;
-    k_ns_put_x<<<T.n ? 2 * ctx->sm_count : 1, 256, 0, st>>>(N.x[k], N.xi[k], N.xv[k], N.counters.p + 1, own.nnz, P->activity_filtering_ratio, bu, own_hdr, T,
+    k_ns_put_x<<<T.n ? 2 * ctx->sm_count : 1, 256, 0, st>>>(N.x[k], N.xi[k], N.xv[k], N.counters.p + 1, own.nnz, N.stats.p + 3, rule, own_hdr, T,
                                                             N.x_epoch, N.counters.p + 2);
     ctx->kernel_launches++;
     if (N.wx) peer_wait_all(ctx, N.wx, N.x_epoch, st);
@@ -645,6 +666,7 @@ static void ns_combine(gt_program* P) {
     cudaStream_t st = ctx->stream;
     const gt_graph* g = P->g;
     GT_CUDA(cudaMemsetAsync(N.counters.p, 0, 2 * sizeof(unsigned int), st));       // heavy count; the frontier count the applicator appends to
+    GT_CUDA(cudaMemsetAsync(N.stats.p + 3, 0, sizeof(unsigned long long), st));     // ... and its size in edges
     const int hgrid = ctx->sm_count * 4;
     const int nper = std::min(N.ntiles, kNsGroup);
     const int gx = std::max(1, ctx->sm_count * 8 / nper);                          // 8 CTAs of 256 threads per SM over the tiles of a launch
@@ -697,7 +719,7 @@ static void ns_apply(gt_program* P, uint32_t iteration, int slot) {
     GT_CUDA(cudaMemsetAsync(P->d_active.p + slot, 0, sizeof(unsigned long long), st));
     if (row.nnz) {
         k_ns_apply<<<grid_for((row.nnz + 3) / 4, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->g->weighted, P->vid0, row.ids.p, row.nnz, N.y[P->own_row_slot],
-                                                                                  iteration, col.bits.p, col.prefix.p, N.x[k], N.xi[k], N.xv[k], N.counters.p + 1,
+                                                                                  iteration, col.bits.p, col.prefix.p, P->g->col_deg[k].p, N.x[k], N.xi[k], N.xv[k], N.counters.p + 1,
                                                                                   P->d_active.p + slot, N.stats.p);
         ctx->kernel_launches++;
     }

@@ -92,6 +92,7 @@ struct gt_program {
     bool initialized = false, converged = false, empty_cleared = false, poisoned = false;
     uint32_t iteration = 0;
     double activity_filtering_ratio = 0.6;        // :194
+    double dense_edge_ratio = 0.5;                // non-stationary: a frontier holding more than this share of the segment's edges runs the dense pass (0 = columns only)
     double bfs_bottom_up_ratio = 0.05;            // BFS on an undirected single-GPU graph: bottom-up pass above this frontier share (0 = never)
     bool timing = false;
     gt_timing tm{};

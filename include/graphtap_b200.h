@@ -250,8 +250,12 @@ GT_API int gt_program_timing(gt_program* p, gt_timing* out);
  * src/vp/vertex_program.hpp:640-684,1018-1054,1611-1637): 0 scatter_gather, 1 combine (the SpMV /
  * SpMSpV over every local tile + the row-group reduce), 2 apply.  Does not advance `iteration`. */
 GT_API int gt_program_run_phase(gt_program* p, int phase);
-/* knobs: name = "activity_filtering_ratio" (default 0.6, :194), "timing" (0/1), "pr_layout"
- * (0 = push over TCSC, 1 = derived pull layout). */
+/* knobs: name = "activity_filtering_ratio" (default 0.6, :194; 1.0 also switches the edge rule below off), "timing" (0/1),
+ * "pr_layout" (0 = push over TCSC, 1 = derived pull layout), "iteration" (the public member, :60),
+ * "dense_edge_ratio" (default 0.5: a frontier holding more than this share of its segment's edges runs the dense pass
+ * although the reference's column rule calls it sparse; 0 = column rule only; results do not depend on it),
+ * "bfs_bottom_up_ratio" (default 0.05: BFS on an undirected single-GPU graph runs bottom-up above this share of active
+ * columns; 0 = never). */
 GT_API int gt_program_set(gt_program* p, const char* name, double value);
 
 #ifdef __cplusplus

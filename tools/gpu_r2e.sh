@@ -1,0 +1,8 @@
+#!/bin/bash
+# multi-GPU validation: tools/multi_gpu_check.py + bench at N = $1
+N=${1:-2}; O=gpurun_out/r2e_n$N; mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555"
+timeout 900 $TR tools/multi_gpu_check.py > $O/check.log 2>&1; echo "check rc=$?" >> $O/check.log
+timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "rc=$?" >> $O/bench.err
+GT_TIMELINE=$O/tl timeout 300 $TR bench.py --gpus $N --steps 1 --warmup 3 --no-other-configs --no-parity > $O/bench_tl.json 2> $O/bench_tl.err
+echo done > $O/done
