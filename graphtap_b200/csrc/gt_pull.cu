@@ -97,8 +97,7 @@ __global__ void k_vrow_make(const uint64_t* __restrict__ rowptr, const uint32_t*
 }
 // per sorted virtual row: start in the CSR key array, length, target row (+ split flag)
 __global__ void k_vrow_meta(const uint64_t* __restrict__ rowptr, const uint32_t* __restrict__ vbase, uint32_t nrows, uint32_t vlen,
-                            const uint32_t* __restrict__ rank_of_v, uint64_t* __restrict__ vstart, uint32_t* __restrict__ vl, uint32_t* __restrict__ vtgt,
-                            const uint8_t* __restrict__ accum_rows) {
+                            const uint32_t* __restrict__ rank_of_v, uint64_t* __restrict__ vstart, uint32_t* __restrict__ vl, uint32_t* __restrict__ vtgt) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
         const uint64_t len = rowptr[r + 1] - rowptr[r];
         const uint32_t b = vbase[r], n = vbase[r + 1] - b;
@@ -106,24 +105,8 @@ __global__ void k_vrow_meta(const uint64_t* __restrict__ rowptr, const uint32_t*
             const uint32_t pos = rank_of_v[b + c];
             vstart[pos] = rowptr[r] + (uint64_t) c * vlen;
             vl[pos] = (uint32_t) std::min<uint64_t>(vlen, len - (uint64_t) c * vlen);
-            vtgt[pos] = r | (n > 1 ? kPullSplit : 0u) | (accum_rows && accum_rows[r] ? kPullAccum : 0u);
+            vtgt[pos] = r | (n > 1 ? kPullSplit : 0u);
         }
-    }
-}
-// rows whose entries in the code range [lo, hi) number at least `min_own` (keys sorted by (row, code), no hot flags)
-__global__ void k_rows_with_own_part(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ rowptr, uint32_t nrows, uint32_t lo, uint32_t hi,
-                                     uint32_t min_own, uint8_t* __restrict__ has_own) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
-        const uint64_t b = rowptr[r], e = rowptr[r + 1];
-        auto lower = [&](uint32_t code) {               // first entry of the row with column code >= code
-            uint64_t l = b, h = e;
-            while (l < h) {
-                const uint64_t m = (l + h) >> 1;
-                if ((uint32_t) keys[m] < code) l = m + 1; else h = m;
-            }
-            return l;
-        };
-        has_own[r] = (lower(hi) - lower(lo)) >= min_own;
     }
 }
 __global__ void k_invert(const uint32_t* __restrict__ perm, uint32_t n, uint32_t* __restrict__ inv) {
@@ -196,8 +179,7 @@ __device__ __forceinline__ double ld_x(const double* __restrict__ x, uint32_t co
 // (profiles/r01_ncu_pull_v0_s22.txt).  Inner loop, per lane: UNROLL independent 4-byte index loads (coalesced
 // across the warp), UNROLL independent 8-byte gathers, UNROLL adds.  One store of y per virtual row; virtual rows
 // of split rows use RED.ADD.
-// ACCUM: 0 = y[t] = acc (first pass over the row), 1 = y[t] += acc (a row's owner lane is unique within a pass),
-// 2 = per virtual row, by its kPullAccum flag (GT_PULL_SPLIT_MIN layouts)
+// ACCUM: 0 = y[t] = acc (first pass over the row), 1 = y[t] += acc (a row's owner lane is unique within a pass)
 template <int UNROLL, bool L1SPLIT, bool L2HINT, int ACCUM>
 __global__ void __launch_bounds__(kPullThreads)
 k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__ slice_ptr, uint32_t nslices,
@@ -225,16 +207,9 @@ k_spmv_pull_sell(const uint32_t* __restrict__ sell, const uint64_t* __restrict__
         const uint32_t v = s * 32 + lane;
         if (v < nv) {
             const uint32_t t = vtgt[v];
-            if (ACCUM == 2) {
-                const uint32_t r = t & ~(kPullSplit | kPullAccum);
-                if (t & kPullSplit) atomicAdd(y + r, acc);
-                else if (t & kPullAccum) y[r] += acc;
-                else y[r] = acc;
-            } else {
-                if (t & kPullSplit) atomicAdd(y + (t & ~kPullSplit), acc);
-                else if (ACCUM) y[t] += acc;          // second pass: a row's owner lane is unique within a pass
-                else y[t] = acc;
-            }
+            if (t & kPullSplit) atomicAdd(y + (t & ~kPullSplit), acc);
+            else if (ACCUM) y[t] += acc;              // later passes: a row's owner lane is unique within a pass
+            else y[t] = acc;
         }
     }
 }
@@ -295,18 +270,9 @@ struct CfPart {
     __device__ bool operator()(const uint64_t& k) const { return kind(k) == want; }
 };
 
-struct OwnPart {                                // entry belongs to the own-chunk part: code inside [lo, hi) and its row is split
-    uint32_t lo, hi; const uint8_t* has_own; bool want;
-    __device__ bool operator()(const uint64_t& k) const {
-        const uint32_t c = (uint32_t) k;
-        return ((c >= lo && c < hi) && has_own[(uint32_t) (k >> 32)]) == want;
-    }
-};
-
 // ---- build ---------------------------------------------------------------------------------------------------
 // (row', code)-sorted keys of one row segment -> virtual rows (<= vrow entries) sorted by decreasing length -> SELL-32
-static void build_sell(gt_ctx* ctx, const uint64_t* sorted, uint64_t total, uint32_t nr, uint32_t kVRow, uint32_t pad_code, PullSell& Q,
-                       const uint8_t* accum_rows = nullptr) {
+static void build_sell(gt_ctx* ctx, const uint64_t* sorted, uint64_t total, uint32_t nr, uint32_t kVRow, uint32_t pad_code, PullSell& Q) {
     cudaStream_t st = ctx->stream;
     Q.nnz = total;
     if (!total || !nr) return;
@@ -349,7 +315,7 @@ static void build_sell(gt_ctx* ctx, const uint64_t* sorted, uint64_t total, uint
         DevBuf<uint64_t> vstart; vstart.alloc(nv);
         DevBuf<uint32_t> vl; vl.alloc(nv);
         Q.vtgt.alloc(nv);
-        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p, accum_rows);
+        k_vrow_meta<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(rowptr.p, vbase.p, nr, kVRow, vpos.p, vstart.p, vl.p, Q.vtgt.p);
         const uint32_t nslices = (nv + 31) / 32;
         DevBuf<uint64_t> sizes; sizes.alloc((size_t) nslices + 1);
         Q.slice_ptr.alloc((size_t) nslices + 1);
@@ -392,9 +358,7 @@ PullLayout* pull_build(gt_graph* g) {
     if (const char* e = getenv("GT_PULL_BAND_SMEM")) P->band_smem = atoi(e) != 0;
     GT_REQUIRE(!P->band_smem || (P->band && P->band <= 28000), "pull layout: GT_PULL_BAND_SMEM needs 0 < GT_PULL_BAND <= 28000 (224 KB of f64)");
     const bool verbose = getenv("GT_PULL_VERBOSE") && atoi(getenv("GT_PULL_VERBOSE"));
-    if (const char* e = getenv("GT_PULL_SPLIT_MIN")) P->split_min = (uint32_t) std::max(0, atoi(e));
     if (const char* e = getenv("GT_PULL_L1HOT")) P->l1hot = (uint32_t) std::max(0, atoi(e));
-    GT_REQUIRE(!P->split_min || !P->l1hot, "pull layout: GT_PULL_SPLIT_MIN needs GT_PULL_L1HOT=0 (column codes without the hot flag)");
     if (const char* e = getenv("GT_PULL_L2HINT")) P->l2hint = atoi(e) != 0;
     if (const char* e = getenv("GT_PULL_UNROLL")) P->unroll = atoi(e) == 4 ? 4 : 8;
     if (const char* e = getenv("GT_PULL_THREADS")) P->threads = std::min(1024, std::max(32, atoi(e) / 32 * 32));
@@ -527,42 +491,24 @@ PullLayout* pull_build(gt_graph* g) {
         uint64_t* rr = sorted;
         uint64_t n_own = 0;
         const bool multi = ctx->comm && comm_size_in(ctx->comm, COMM_COLGRP) > 1;
-        DevBuf<uint8_t> has_own;                               // GT_PULL_SPLIT_MIN: rows that get an own-chunk part
         if ((multi || P->band) && n_rr) {
             const uint32_t lo = multi ? P->xoff[g->lay.info.accu_segment_col] : 0, hi = multi ? lo + P->xchunk : P->band;
             DevBuf<unsigned long long> d_n; d_n.alloc(2);
             unsigned long long h_n = 0;
-            if (P->split_min) {
-                DevBuf<uint64_t> rowptr; rowptr.alloc((size_t) nr + 1);
-                has_own.alloc(nr);
-                k_row_ptr<<<grid_for((uint64_t) nr + 1, 256, ctx->sm_count), 256, 0, st>>>(sorted, n_rr, nr, rowptr.p);
-                k_rows_with_own_part<<<grid_for(nr, 256, ctx->sm_count), 256, 0, st>>>(sorted, rowptr.p, nr, lo, hi, P->split_min, has_own.p);
-                ctx->kernel_launches += 2;
-                size_t tb = 0;
-                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, true}, st));
-                DevBuf<uint8_t> tmp; tmp.alloc(tb);
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, true}, st));
-                GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
-                GT_CUDA(cudaStreamSynchronize(st));
-                n_own = h_n;
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) n_rr, OwnPart{lo, hi, has_own.p, false}, st));
-                GT_CUDA(cudaStreamSynchronize(st));
-            } else {
-                size_t tb = 0;
-                GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
-                DevBuf<uint8_t> tmp; tmp.alloc(tb);
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
-                GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
-                GT_CUDA(cudaStreamSynchronize(st));
-                n_own = h_n;
-                GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) n_rr, CodeInRange{lo, hi, false}, st));
-                GT_CUDA(cudaStreamSynchronize(st));
-            }
+            size_t tb = 0;
+            GT_CUDA(cub::DeviceSelect::If(nullptr, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
+            DevBuf<uint8_t> tmp; tmp.alloc(tb);
+            GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other, d_n.p, (int64_t) n_rr, CodeInRange{lo, hi, true}, st));
+            GT_CUDA(cudaMemcpyAsync(&h_n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+            GT_CUDA(cudaStreamSynchronize(st));
+            n_own = h_n;
+            GT_CUDA(cub::DeviceSelect::If(tmp.p, tb, sorted, other + n_own, d_n.p + 1, (int64_t) n_rr, CodeInRange{lo, hi, false}, st));
+            GT_CUDA(cudaStreamSynchronize(st));
             ctx->kernel_launches += 2;
             rr = other;
         }
         if (n_own) build_sell(ctx, rr, n_own, nr, vrow_for(n_own), pad_code, Q.own);
-        build_sell(ctx, rr + n_own, n_rr - n_own, nr, vrow_for(n_rr - n_own), pad_code, Q.rest, P->split_min ? has_own.p : nullptr);
+        build_sell(ctx, rr + n_own, n_rr - n_own, nr, vrow_for(n_rr - n_own), pad_code, Q.rest);
         if (n_rs) build_sell(ctx, cf_tail, n_rs, nr, vrow_for(n_rs), pad_code, Q.snk);
         if (n_sx) build_sell(ctx, cf_tail + n_rs, n_sx, nr, vrow_for(n_sx), pad_code, Q.src);
         if (verbose)
@@ -588,7 +534,7 @@ void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, co
     // y is zero-filled before the pass.  Only the first part launched may use the plain store: every SELL array carries a
     // (possibly empty) virtual row for EVERY row of the segment, so a later part that stored instead of adding would wipe
     // the rows that merely share its last slice — the hottest ones, which sort first among the empty rows.
-    const int accum = (part == 1 && R.own.nslices > 0) ? (P->split_min ? 2 : 1) : part >= 2 ? 1 : 0;
+    const int accum = (part == 1 && R.own.nslices > 0) || part >= 2;
     if (!Q.nslices) return;
     if (part == 0 && P->band_smem) {                  // hot band from shared memory: one CTA per SM, the whole carve-out
         const size_t smem = (size_t) P->band * sizeof(double);
@@ -604,7 +550,7 @@ void pull_spmv(gt_ctx* ctx, const PullLayout* P, uint32_t row_slot, int part, co
     }
     const int grid = ctx->sm_count * P->ctas_per_sm;
 #define GT_PULL_LAUNCH(U, A, B, C) k_spmv_pull_sell<U, A, B, C><<<grid, P->threads, 0, ctx->stream>>>(Q.sell.p, Q.slice_ptr.p, Q.nslices, Q.vtgt.p, Q.nv, x, y)
-#define GT_PULL_AB(U, A, B) do { if (accum == 2) GT_PULL_LAUNCH(U, A, B, 2); else if (accum) GT_PULL_LAUNCH(U, A, B, 1); else GT_PULL_LAUNCH(U, A, B, 0); } while (0)
+#define GT_PULL_AB(U, A, B) do { if (accum) GT_PULL_LAUNCH(U, A, B, 1); else GT_PULL_LAUNCH(U, A, B, 0); } while (0)
     const bool split = P->l1hot > 0;
     if (P->unroll == 4) {
         if (split) { if (P->l2hint) GT_PULL_AB(4, true, true); else GT_PULL_AB(4, true, false); }

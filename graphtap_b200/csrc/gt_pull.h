@@ -7,7 +7,6 @@ namespace gt {
 constexpr uint32_t kPullMaxSegs = 8;            // local column segments per rank (rank_ncolgrps: 1,2,2,4 at p = 1,2,4,8)
 constexpr uint32_t kPullVRow = 512;             // longest run of entries one lane sums before the row is split (GT_PULL_VROW)
 constexpr uint32_t kPullSplit = 0x80000000u;    // vtgt flag: partial sum of a split row -> RED.ADD
-constexpr uint32_t kPullAccum = 0x40000000u;    // vtgt flag (GT_PULL_SPLIT_MIN layouts only): this row also has an own-chunk part -> y +=
 constexpr uint32_t kPullHotBit = 0x80000000u;   // column-code flag: one of the hottest columns -> L1-allocating gather
 constexpr int kPullThreads = 1024;
 
@@ -45,10 +44,6 @@ struct PullLayout {
     uint32_t ychunk = 0, ylen = 0;
     std::vector<PullRows> rows;                 // per row slot
     uint32_t vrow = kPullVRow;                  // tuning knobs, fixed at build time (GT_PULL_* environment)
-    // Multi-GPU experiment (default 0 = every row with an own-chunk entry is split in an own and a rest part): rows with
-    // fewer than `split_min` entries in this rank's own x chunk keep ALL their entries in the rest part, so only rows
-    // that are long enough to amortise a second y access are touched twice.
-    uint32_t split_min = 0;
     uint32_t band = 0;                          // single GPU: columns [0, band) of the hot order form a pass of their own (0 = one pass)
     bool band_smem = false;                     // GT_PULL_BAND_SMEM: that pass gathers from a shared-memory copy of x[0, band)
     uint32_t l1hot = 0;                         // hottest columns (per rank) gathered L1::evict_last, the rest L1::evict_first; 0 = no distinction
