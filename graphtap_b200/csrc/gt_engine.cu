@@ -444,7 +444,7 @@ static void pull_state_out(gt_program* P) {
 //  * every put is consumed (its counter waited for) before execute() / run_phase() returns, so a window is never
 //    written after its owner could have freed it.
 // x buffer the current iteration reads (parity of the last put) / the one the next messenger writes
-static void tl_mark(gt_program* P, const char* tag, cudaStream_t s) {
+void tl_mark(gt_program* P, const char* tag, cudaStream_t s) {
     if (!P->timeline_on) return;
     cudaEvent_t ev;
     if (!P->timeline_pool.empty()) { ev = P->timeline_pool.back(); P->timeline_pool.pop_back(); }
@@ -452,7 +452,7 @@ static void tl_mark(gt_program* P, const char* tag, cudaStream_t s) {
     GT_CUDA(cudaEventRecord(ev, s));
     P->timeline.push_back({ev, tag, P->iteration});
 }
-static void tl_dump(gt_program* P) {
+void tl_dump(gt_program* P) {
     if (!P->timeline_on) return;
     const char* prefix = getenv("GT_TIMELINE");
     std::string path = std::string(prefix ? prefix : "gt_timeline") + ".r" + std::to_string(P->ctx->rank) + ".jsonl";
@@ -733,6 +733,7 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         else if (n == "pr_layout") { p->pr_layout = (int) value; p->initialized = false; }
         else if (n == "bfs_bottom_up_ratio") p->bfs_bottom_up_ratio = value;
         else if (n == "dense_edge_ratio") p->dense_edge_ratio = value;
+        else if (n == "sparse_apply") p->sparse_apply = value != 0;
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
 }
@@ -767,6 +768,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         p->tm.scatter_gather_ms = p->tm.combine_ms = p->tm.apply_ms = 0;
         if (!p->stationary) {
+            p->timeline_on = getenv("GT_TIMELINE") != nullptr;
             gt::ns_execute(p, num_iterations);            // records ev1, drains the stream
         } else {
             const bool peer_used = p->wx || p->wy;

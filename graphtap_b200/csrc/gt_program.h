@@ -93,6 +93,7 @@ struct gt_program {
     uint32_t iteration = 0;
     double activity_filtering_ratio = 0.6;        // :194
     double dense_edge_ratio = 0.5;                // non-stationary: a frontier holding more than this share of the segment's edges runs the dense pass (0 = columns only)
+    bool sparse_apply = true;                     // non-stationary: after the first pass the applicator visits only the rows whose y improved
     double bfs_bottom_up_ratio = 0.05;            // BFS on an undirected single-GPU graph: bottom-up pass above this frontier share (0 = never)
     bool timing = false;
     gt_timing tm{};
@@ -108,6 +109,10 @@ template <typename T>
 __global__ void k_fill(T* p, T v, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) p[i] = v;
 }
+
+// GT_TIMELINE marks (gt_engine.cu)
+void tl_mark(gt_program* P, const char* tag, cudaStream_t s);
+void tl_dump(gt_program* P);
 
 // non-stationary engine (gt_ns.cu)
 void ns_alloc(gt_program* P);                      // buffers, windows, tile descriptors
