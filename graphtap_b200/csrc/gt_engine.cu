@@ -733,7 +733,6 @@ extern "C" int gt_program_set(gt_program* p, const char* name, double value) {
         else if (n == "pr_layout") { p->pr_layout = (int) value; p->initialized = false; }
         else if (n == "bfs_bottom_up_ratio") p->bfs_bottom_up_ratio = value;
         else if (n == "dense_edge_ratio") p->dense_edge_ratio = value;
-        else if (n == "sparse_apply") p->sparse_apply = value != 0;
         else throw gt::Error(GT_ERR_INVALID, "gt_program_set: unknown knob " + n);
     });
 }

@@ -71,11 +71,7 @@ struct NsState {
     std::vector<uint32_t*> x, xi, xv;            // per x slot
     DevBuf<uint32_t> Y;                          // R x ychunk
     std::vector<uint32_t*> y;
-    DevBuf<uint8_t> T;                           // improved-row flags, R x ychunk: the follower segments' feed the y exchange, the owned segment's the sparse applicator
-    DevBuf<uint32_t> act;                        // vertices whose applicator returned true in the last pass
-    DevBuf<unsigned int> nact;                   // [2], by pass parity
-    int act_parity = 0;
-    bool sparse_ready = false;                   // the last applicator pass left C, x and `act` consistent for a sparse pass
+    DevBuf<uint8_t> T;                           // improved-row flags, R x ychunk (used for the slots this rank does not lead)
     DevBuf<uint32_t> ystage;                     // (yi, yv) staging, 2 x ychunk per send slot
     DevBuf<NsTile> tiles; int ntiles = 0;        // device copy (the heavy-column kernel indexes it by list entry)
     std::vector<NsTile> htiles;                  // host copy, handed to the tile passes by value
@@ -329,7 +325,7 @@ k_ns_bfs_bottom_up(const __grid_constant__ NsTiles tiles, const uint32_t* __rest
         for (uint32_t i = b; i < e; i++) {
             const uint32_t xv = Q.x[Q.IA[i]];
             bytes += 8;
-            if (xv != GT_INF_U32) { Q.y[j] = xv; Q.t[j] = 1; break; }
+            if (xv != GT_INF_U32) { Q.y[j] = xv; break; }
         }
     }
 #pragma unroll
@@ -387,51 +383,43 @@ __global__ void __launch_bounds__(256) k_ns_put_y(const NsYSend* __restrict__ se
         *(volatile uint32_t*) Q.dst_flag = epoch & (kPeerSeqLen - 1);
     }
 }
-__global__ void __launch_bounds__(256) k_ns_merge_y(const NsYRecv* __restrict__ recvs, uint32_t* __restrict__ y, uint8_t* __restrict__ t) {
+__global__ void __launch_bounds__(256) k_ns_merge_y(const NsYRecv* __restrict__ recvs, uint32_t* __restrict__ y) {
     const NsYRecv Q = recvs[blockIdx.y];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (Q.hdr[0] == NS_SPARSE) {
         const uint32_t k = Q.hdr[1];
-        for (uint32_t i = tid; i < k; i += nth) { const uint32_t r = Q.yi[i], v = Q.yv[i]; if (v < atomicMin(y + r, v)) t[r] = 1; }     // :1559-1562
+        for (uint32_t i = tid; i < k; i += nth) atomicMin(y + Q.yi[i], Q.yv[i]);                     // :1559-1562
     } else {
-        for (uint32_t i = tid; i < Q.n; i += nth) { const uint32_t v = Q.dense[i]; if (v < y[i] && v < atomicMin(y + i, v)) t[i] = 1; }   // :1568-1569
+        for (uint32_t i = tid; i < Q.n; i += nth) { const uint32_t v = Q.dense[i]; if (v < y[i]) atomicMin(y + i, v); }   // :1568-1569
     }
 }
 
 // ---- apply ------------------------------------------------------------------------------------------------------------------
 // applicator on the rows of rowgrp_nnz_rows (:1739-1751,1768-1780), fused with the next iteration's messenger and frontier
 // compaction: a vertex is active next iteration iff its applicator returned true now.
-// SPARSE: only the rows whose y IMPROVED in this iteration are visited (the `t` flags the tile passes and the merge set).
-// For every other row the reference's applicator would find y unchanged since the row was last applied and return false
-// (BFS: an unvisited row's y is still infinity(); CC / SSSP: state <= y already), so the only thing it does there is
-// clearing last iteration's activity flag — k_ns_apply_reset does that from the list of the vertices that were active.
-template <bool SPARSE>
+// (A pass over only the rows whose y improved was built and measured: with the flag traffic it adds to the tile passes
+// and its reset pass it LOSES on one GPU — SSSP RMAT-25 12.3 vs 11.4 ms, BFS RMAT-22 0.67 vs 0.51 ms,
+// profiles/r02_ncu_ns_sssp25_sparse_apply_experiment.csv — so the applicator walks every non-empty row, as the reference does.)
 __global__ void __launch_bounds__(256)
 k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __restrict__ IR, uint32_t nr, const uint32_t* __restrict__ y, uint32_t iteration,
            const uint8_t* __restrict__ J, const uint32_t* __restrict__ JV, const uint32_t* __restrict__ cdeg, uint32_t* __restrict__ x,
-           uint32_t* __restrict__ xi, uint32_t* __restrict__ xv, unsigned int* __restrict__ count, uint8_t* __restrict__ t_own,
-           uint32_t* __restrict__ act, unsigned int* __restrict__ nact, unsigned long long* __restrict__ active, unsigned long long* __restrict__ stats) {
+           uint32_t* __restrict__ xi, uint32_t* __restrict__ xv, unsigned int* __restrict__ count, unsigned long long* __restrict__ active,
+           unsigned long long* __restrict__ stats) {
     typedef cub::BlockScan<unsigned, 256> BS;
     __shared__ typename BS::TempStorage tmp;
-    __shared__ unsigned base_s, base_a;
+    __shared__ unsigned base_s;
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats[2]) { stats[1]++; stats[2] = 0; }
     unsigned changed = 0;
     unsigned long long fe = 0;                                         // the next frontier's size in edges -> stats[3]
     const uint32_t per_iter = 256 * 4;
     for (uint32_t start = blockIdx.x * per_iter; start < nr; start += gridDim.x * per_iter) {
-        uint32_t cj[4], cm[4], cv[4];
-        unsigned mine = 0, mine_a = 0;
-        uint32_t f4 = 0xffffffffu;
-        if (SPARSE) {
-            const uint32_t r0 = start + threadIdx.x * 4;               // the flags are padded to a multiple of 4 rows
-            f4 = r0 < nr ? *reinterpret_cast<const uint32_t*>(t_own + r0) : 0u;
-            if (f4) *reinterpret_cast<uint32_t*>(t_own + r0) = 0u;      // cleared for the next iteration (:1795-1801)
-        }
+        uint32_t cj[4], cm[4];
+        unsigned mine = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const uint32_t r = SPARSE ? start + threadIdx.x * 4 + u : start + u * 256 + threadIdx.x;
-            cj[u] = 0xffffffffu; cv[u] = 0xffffffffu;
-            if (r >= nr || (SPARSE && !((f4 >> (8 * u)) & 0xffu))) continue;
+            const uint32_t r = start + u * 256 + threadIdx.x;
+            cj[u] = 0xffffffffu;
+            if (r >= nr) continue;
             const uint32_t v = IR[r];
             const uint32_t yy = y[r];
             bool ch = false;
@@ -451,29 +439,21 @@ k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __res
             }
             V.C[v] = ch;
             changed += ch;
-            if (ch) { cv[u] = v; mine_a++; }
             if (J[v]) {                                                // the vertex has a column: next iteration's x (:737-751)
                 const uint32_t j = JV[v];
                 x[j] = ch ? msg : GT_INF_U32;
                 if (ch) { cj[u] = j; cm[u] = msg; mine++; fe += cdeg[v]; }
             }
         }
-        unsigned off, total, off_a, total_a;
+        unsigned off, total;
         BS(tmp).ExclusiveSum(mine, off, total);
+        if (threadIdx.x == 0 && total) base_s = atomicAdd(count, total);
         __syncthreads();
-        BS(tmp).ExclusiveSum(mine_a, off_a, total_a);
-        if (threadIdx.x == 0) {
-            if (total) base_s = atomicAdd(count, total);
-            if (total_a) base_a = atomicAdd(nact, total_a);
-        }
-        __syncthreads();
-        if (mine_a) {
-            unsigned pos = base_s + off, pa = base_a + off_a;
+        if (mine) {
+            unsigned pos = base_s + off;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 4; u++)
                 if (cj[u] != 0xffffffffu) { xi[pos] = cj[u]; xv[pos] = cm[u]; pos++; }
-                if (cv[u] != 0xffffffffu) act[pa++] = cv[u];
-            }
         }
         __syncthreads();
     }
@@ -484,17 +464,6 @@ k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __res
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) fe += __shfl_xor_sync(0xffffffffu, fe, o);
     if ((threadIdx.x & 31) == 0 && fe) atomicAdd(stats + 3, fe);
-}
-// before a sparse applicator pass: last iteration's active vertices lose their flag and their x (those that stay
-// active get both back from the pass); k = the size of the frontier this iteration consumed (the owner's header)
-__global__ void k_ns_apply_reset(const uint32_t* __restrict__ xi, const uint32_t* __restrict__ own_hdr, uint32_t* __restrict__ x,
-                                 const uint32_t* __restrict__ act, const unsigned int* __restrict__ nact_prev, uint8_t* __restrict__ C,
-                                 unsigned int* __restrict__ nact_next) {
-    const uint32_t k = own_hdr[1], na = *nact_prev;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    for (uint32_t i = tid; i < k; i += nth) x[xi[i]] = GT_INF_U32;
-    for (uint32_t i = tid; i < na; i += nth) C[act[i]] = 0;
-    if (tid == 0) *nact_next = 0;
 }
 // After the first applicator pass: vertices whose row is empty everywhere take applicator(state) -> false (:1726-1738,
 // :38), so they are never active again and their x stays infinity() from now on.
@@ -553,11 +522,11 @@ void ns_alloc(gt_program* P) {
     for (size_t k = 0; k < N.R; k++) N.y[k] = N.Y.p + (size_t) N.yq[k] * N.ychunk;
     // tiles
     N.ntiles = (int) g->tiles.size();
-    N.T.alloc(N.R * N.ychunk);
-    GT_CUDA(cudaMemsetAsync(N.T.p, 0, N.T.bytes(), st));
-    N.act.alloc(std::max<size_t>(1, (*P->prow)[P->own_row_slot].nnz));
-    N.nact.alloc(2);
-    GT_CUDA(cudaMemsetAsync(N.nact.p, 0, N.nact.bytes(), st));
+    const bool y_sparse = N.wy != nullptr;
+    if (y_sparse) {
+        N.T.alloc(N.R * N.ychunk);
+        GT_CUDA(cudaMemsetAsync(N.T.p, 0, N.T.bytes(), st));
+    }
     std::vector<NsTile> ht(N.ntiles);
     uint64_t nnz_all = 0;
     for (int k = 0; k < N.ntiles; k++) {
@@ -567,7 +536,7 @@ void ns_alloc(gt_program* P) {
         Q.nnz = T.nnz; Q.nchunks = (uint32_t) ((T.nnz + GT_PUSH_CHUNK - 1) / GT_PUSH_CHUNK); Q.ncols = g->cols[T.col_slot].nnz;
         Q.x = N.x[T.col_slot]; Q.xi = N.xi[T.col_slot]; Q.xv = N.xv[T.col_slot]; Q.hdr = N.hdr + 4 * (size_t) N.xq[T.col_slot];
         Q.y = N.y[T.row_slot];
-        Q.t = N.T.p + (size_t) N.yq[T.row_slot] * N.ychunk;
+        Q.t = (y_sparse && (int) T.row_slot != P->own_row_slot) ? N.T.p + (size_t) N.yq[T.row_slot] * N.ychunk : nullptr;
         Q.dense_bytes = T.nnz ? (g->weighted ? 8ull : 4ull) * T.nnz + 4ull * ((uint64_t) Q.ncols + 1) + 4ull * Q.ncols : 0;
         N.any_heavy |= T.max_col_entries > kNsHeavyColumn;
         nnz_all += T.nnz;
@@ -640,8 +609,7 @@ void ns_initialize(gt_program* P) {            // Y starts at infinity() (:625-6
     NsState& N = *P->ns;
     k_fill<uint32_t><<<grid_for(N.Y.n, 256, ctx->sm_count), 256, 0, ctx->stream>>>(N.Y.p, GT_INF_U32, N.Y.n);
     ctx->kernel_launches++;
-    GT_CUDA(cudaMemsetAsync(N.T.p, 0, N.T.bytes(), ctx->stream));
-    N.sparse_ready = false;
+    if (N.T.p) GT_CUDA(cudaMemsetAsync(N.T.p, 0, N.T.bytes(), ctx->stream));
     GT_CUDA(cudaGetLastError());
 }
 
@@ -757,7 +725,7 @@ static void ns_combine(gt_program* P) {
         tl_mark(P, "y_put", st);
         peer_wait_all(ctx, N.wy, N.y_epoch, st);
         tl_mark(P, "y_arrived", st);
-        k_ns_merge_y<<<dim3(ctx->sm_count, N.nrecv), 256, 0, st>>>(N.yrecv.p, N.y[P->own_row_slot], N.T.p + (size_t) N.yq[P->own_row_slot] * N.ychunk);
+        k_ns_merge_y<<<dim3(ctx->sm_count, N.nrecv), 256, 0, st>>>(N.yrecv.p, N.y[P->own_row_slot]);
         ctx->kernel_launches += 3;
     } else if (ctx->comm && N.G > 1) {
         comm_reduce_scatter_inplace(ctx->comm, P->reduce_group, N.Y.p, N.ychunk, CT_U32, CO_MIN, st);
@@ -773,28 +741,11 @@ static void ns_apply(gt_program* P, uint32_t iteration, int slot) {
     const SegMaps& row = (*P->prow)[P->own_row_slot];
     const SegMaps& col = (*P->pcol)[P->own_col_slot];
     const int k = P->own_col_slot;
-    uint8_t* t_own = N.T.p + (size_t) N.yq[P->own_row_slot] * N.ychunk;
-    uint32_t* own_hdr = N.hdr + 4 * (size_t) N.xq[k];
     if (row.nnz) {
-        const int grid = grid_for((row.nnz + 3) / 4, 256, ctx->sm_count);
-        unsigned int* nact = N.nact.p + N.act_parity;
-        if (N.sparse_ready && P->sparse_apply) {
-            k_ns_apply_reset<<<ctx->sm_count, 256, 0, st>>>(N.xi[k], own_hdr, N.x[k], N.act.p, N.nact.p + (N.act_parity ^ 1), P->C.p, nact);
-            k_ns_apply<true><<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, P->vid0, row.ids.p, row.nnz, N.y[P->own_row_slot], iteration, col.bits.p,
-                                                  col.prefix.p, P->g->col_deg[k].p, N.x[k], N.xi[k], N.xv[k], N.counters.p + 1, t_own, N.act.p, nact,
-                                                  P->d_active.p + slot, N.stats.p);
-            ctx->kernel_launches += 2;
-        } else {
-            // the first pass of an execute() (C and x come from the caller's state) visits every non-empty row (:1726-1767)
-            GT_CUDA(cudaMemsetAsync(nact, 0, sizeof(unsigned int), st));
-            k_ns_apply<false><<<grid, 256, 0, st>>>(P->vs(), P->app, P->g->weighted, P->vid0, row.ids.p, row.nnz, N.y[P->own_row_slot], iteration, col.bits.p,
-                                                   col.prefix.p, P->g->col_deg[k].p, N.x[k], N.xi[k], N.xv[k], N.counters.p + 1, t_own, N.act.p, nact,
-                                                   P->d_active.p + slot, N.stats.p);
-            GT_CUDA(cudaMemsetAsync(t_own, 0, N.ychunk, st));
-            ctx->kernel_launches++;
-        }
-        N.act_parity ^= 1;
-        N.sparse_ready = true;
+        k_ns_apply<<<grid_for((row.nnz + 3) / 4, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->g->weighted, P->vid0, row.ids.p, row.nnz, N.y[P->own_row_slot],
+                                                                                  iteration, col.bits.p, col.prefix.p, P->g->col_deg[k].p, N.x[k], N.xi[k], N.xv[k], N.counters.p + 1,
+                                                                                  P->d_active.p + slot, N.stats.p);
+        ctx->kernel_launches++;
     }
     if (!P->empty_cleared) {
         k_ns_clear_empty<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->C.p, row.bits.p, col.bits.p, col.prefix.p, P->th, N.x[k]);
@@ -837,7 +788,6 @@ void ns_execute(gt_program* P, uint32_t num_iterations) {
         acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
     GT_CUDA(cudaMemsetAsync(N.stats.p, 0, 3 * sizeof(unsigned long long), st));
-    N.sparse_ready = false;                              // C and x are rebuilt from the caller's state below
     if (peer) peer_fence_world(ctx, st);                 // every rank has left whatever used the windows before (run_phase, an earlier execute)
     timed(P->tm.scatter_gather_ms, [&] { ns_x_from_state(P); });
     const uint32_t it0 = P->iteration;
@@ -883,7 +833,6 @@ void ns_run_phase(gt_program* P, int phase) {
     gt_ctx* ctx = P->ctx;
     NsState& N = *P->ns;
     N.active_slot = 0;
-    N.sparse_ready = false;
     if (phase == 0) {
         if (N.wx || N.wy) peer_fence_world(ctx, ctx->stream);
         ns_x_from_state(P);

@@ -93,7 +93,6 @@ struct gt_program {
     uint32_t iteration = 0;
     double activity_filtering_ratio = 0.6;        // :194
     double dense_edge_ratio = 0.5;                // non-stationary: a frontier holding more than this share of the segment's edges runs the dense pass (0 = columns only)
-    bool sparse_apply = true;                     // non-stationary: after the first pass the applicator visits only the rows whose y improved
     double bfs_bottom_up_ratio = 0.05;            // BFS on an undirected single-GPU graph: bottom-up pass above this frontier share (0 = never)
     bool timing = false;
     gt_timing tm{};

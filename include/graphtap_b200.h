@@ -254,8 +254,6 @@ GT_API int gt_program_run_phase(gt_program* p, int phase);
  * "pr_layout" (0 = push over TCSC, 1 = derived pull layout), "iteration" (the public member, :60),
  * "dense_edge_ratio" (default 0.5: a frontier holding more than this share of its segment's edges runs the dense pass
  * although the reference's column rule calls it sparse; 0 = column rule only; results do not depend on it),
- * "sparse_apply" (default 1: after the first pass of an execute() the applicator visits only the rows whose y improved;
- * 0 = every non-empty row every iteration, as the reference walks them; same states either way),
  * "bfs_bottom_up_ratio" (default 0.05: BFS on an undirected single-GPU graph runs bottom-up above this share of active
  * columns; 0 = never). */
 GT_API int gt_program_set(gt_program* p, const char* name, double value);

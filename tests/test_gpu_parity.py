@@ -542,31 +542,3 @@ def test_pagerank_cf_schedule_at_scale_20():
         assert (out[E._TCSC_]["degree"] == out[E._TCSC_CF_]["degree"]).all()
         rel = np.abs(out[E._TCSC_]["rank"] - out[E._TCSC_CF_]["rank"]) / out[E._TCSC_]["rank"]
         assert rel.max() <= 1e-12, (iters, rel.max())
-
-
-def test_sparse_applicator_equals_full_applicator():
-    """After the first pass the applicator visits only the rows whose y improved ("sparse_apply", default on).  States,
-    iteration counts and the behaviour across execute() calls must be those of the pass over every non-empty row."""
-    from graphtap_b200.rmat import rmat_edges
-    E, O = _E(), _O()
-    tri = rmat_edges(16, seed=21, weighted=True)
-    n = 1 << 16
-    specs = (("bfs", E.BFS_Program, False, dict(directed=False, transpose=False, self_loops=False, parallel_edges=False), (False, False, True)),
-             ("cc", E.CC_Program, False, dict(directed=False, transpose=False, self_loops=True, parallel_edges=False), (False, True, False)),
-             ("sssp", E.SSSP_Program, True, dict(directed=True, transpose=True, self_loops=False, parallel_edges=False), (False, True, False)))
-    for app, mk, w, fl, flags in specs:
-        ref, rit = O.run_app(app, tri if w else tri[:, :2].copy(), n, 1, None if app == "cc" else 0)
-        G = E.Graph(weighted=w)
-        G.load_triples(tri if w else tri[:, :2].copy(), n, **fl)
-        for sparse in (0, 1):
-            V = mk(G, *flags, E._ROW_)
-            V.set("sparse_apply", sparse)
-            V.set("bfs_bottom_up_ratio", 0.0)
-            assert V.execute() == rit, (app, sparse)
-            assert_states(app, V.V, ref, n + 1)
-            V.free()
-        V = mk(G, *flags, E._ROW_)                 # in pieces: every execute() starts with a full pass again
-        V.execute(2); V.execute(3)
-        assert V.execute() == rit
-        assert_states(app, V.V, ref, n + 1)
-        V.free(); G.free()
