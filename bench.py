@@ -387,20 +387,26 @@ def run_ours(args):
     capi.check(L.gt_host_alloc_pinned(sb, C.byref(pin_out)))
     P.initialize(D)
     capi.check(L.gt_program_state_to_host(P.handle, pin_in, sb))        # the initial states, on the host
-    e2e_ms = []
+    e2e_ms, parts = [], [0.0, 0.0, 0.0]
     for s in range(min(2, args.warmup) + args.steps):
         E.Env.barrier()
         t0 = time.perf_counter()
-        capi.check(L.gt_program_state_from_host(P.handle, pin_in, sb))  # H2D from pinned memory
+        capi.check(L.gt_program_state_from_host(P.handle, pin_in, sb))  # H2D from pinned memory (synchronises)
+        t1 = time.perf_counter()
         P.set("iteration", 0)
         capi.check(L.gt_program_execute(P.handle, ITERS, None))
+        t2 = time.perf_counter()
         capi.check(L.gt_program_state_to_host(P.handle, pin_out, sb))   # D2H (synchronises)
-        dt = (time.perf_counter() - t0) * 1e3
+        t3 = time.perf_counter()
         if s >= min(2, args.warmup):
-            e2e_ms.append(dt)
+            e2e_ms.append((t3 - t0) * 1e3)
+            for k, d in enumerate((t1 - t0, t2 - t1, t3 - t2)):
+                parts[k] += d * 1e3 / args.steps
     e2e_total = red.max(sum(e2e_ms)) * 1e-3
+    # where a step's wall time goes on the slowest rank of each part (host clock; every call ends with the stream drained)
     e2e = {"value": nnz * ITERS * args.steps / e2e_total / 1e9, "unit": UNIT, "h2d_bytes_per_step": sb * nranks, "d2h_bytes_per_step": sb * nranks,
-           "ms_per_step": 1e3 * e2e_total / args.steps}
+           "ms_per_step": 1e3 * e2e_total / args.steps,
+           "parts_ms": {"state_from_host": red.max(parts[0]), "execute": red.max(parts[1]), "state_to_host": red.max(parts[2])}}
     out_states = np.frombuffer((C.c_char * sb).from_address(pin_out.value), dtype=E.PR_STATE)
     # Vertex_Program::checksum's vertex range (vid < nrows, :1936); the sums are the same numbers at every N up to f64
     # summation order, so N = 1, 2, 4, 8 can be compared directly

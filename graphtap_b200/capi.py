@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgraphtap_b200.so")
+# GT_LIB: another build of the same library (tools/build_variants.sh: compile-time A/B experiments), never a fallback
+LIB_PATH = os.environ.get("GT_LIB") or os.path.join(_HERE, "libgraphtap_b200.so")
 
 # enums (include/graphtap_b200.h)
 GT_OK, GT_ERR_INVALID, GT_ERR_NO_DEVICE, GT_ERR_CUDA, GT_ERR_NCCL, GT_ERR_OOM, GT_ERR_UNSUPPORTED = range(7)
@@ -89,6 +90,8 @@ PROTOTYPES = {
     "gt_layout_table": (C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_uint32)]),
     "gt_graph_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
     "gt_graph_build_rmat": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
+    "gt_graph_build_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
+    "gt_graph_build_rmat_partitioned": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
     "gt_rmat_generate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "gt_graph_free": (C.c_int, [C.c_void_p]),
     "gt_graph_info_get": (C.c_int, [C.c_void_p, C.POINTER(GraphInfo)]),
@@ -110,6 +113,7 @@ PROTOTYPES = {
     "gt_program_state_from_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "gt_program_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gt_program_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
+    "gt_program_timing_samples": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32)]),
     "gt_program_run_phase": (C.c_int, [C.c_void_p, C.c_int]),
     "gt_program_set": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
 }

@@ -111,6 +111,12 @@ struct IngestParams {
     unsigned long long* counters;    // [0] owned entries, [1] append cursor, [2] out-of-range records
     uint64_t* keys;                  // fill pass
     uint32_t* wts;                   // fill pass, weighted
+    // partitioned ingest (every rank holds a share of the records): route every entry to the rank that owns its tile
+    const int32_t* tile_rank;        // [p*p] owner of every tile (after the leader swap)
+    unsigned long long* dest_count;  // [nranks] entries per destination (count pass) / running cursors (fill pass)
+    const unsigned long long* dest_off;   // [nranks] first slot of every destination in the send buffer
+    uint32_t* sendbuf;               // {row, col[, w]} records grouped by destination
+    int no_marks;                    // the records are already-routed entries: marks and degrees came from the all-reduce
 };
 
 template <bool FILL>
@@ -122,7 +128,7 @@ __device__ __forceinline__ void ingest_emit(const IngestParams& Q, uint32_t r, u
         rg = r / Q.th;
         cg = c / Q.th;
         t = Q.tile_local[rg * Q.p + cg];
-        if (!FILL) { Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.rdeg_all + r, 1u); atomicAdd(Q.cdeg_all + c, 1u); }
+        if (!FILL && !Q.no_marks) { Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.rdeg_all + r, 1u); atomicAdd(Q.cdeg_all + c, 1u); }
     }
     const bool own = valid && t >= 0;
     if (!FILL) {
@@ -142,6 +148,55 @@ __device__ __forceinline__ void ingest_emit(const IngestParams& Q, uint32_t r, u
             }
         }
     }
+}
+
+// Partitioned ingest (every rank holds a SHARE of the records, as Graph::parread_binary reads 1/p of the file,
+// src/mat/graph.hpp:307-335): apply the per-edge flags (:337-356) to this rank's share and route every resulting entry
+// to the rank that owns its tile (Matrix::distribute, src/mat/matrix.hpp:692-810).  Count pass: entries per destination +
+// this share's row / column marks and degrees (all-reduced over the world afterwards, where the reference OR-reduces
+// its bitmaps along the groups, :973-1083).  Fill pass: {row, col[, w]} records into the send buffer, grouped by
+// destination (the order inside a group is irrelevant: the owner sorts).  Counters are bumped once per warp and
+// destination (__match_any), not once per entry.
+template <bool FILL>
+__device__ __forceinline__ void route_emit(const IngestParams& Q, uint32_t r, uint32_t c, uint32_t w, bool valid) {
+    const int dest = valid ? Q.tile_rank[(r / Q.th) * Q.p + (c / Q.th)] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, dest);
+    if (!valid) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(Q.dest_count + dest, (unsigned long long) __popc(peers));
+    if (!FILL) {
+        Q.I_all[r] = 1; Q.J_all[c] = 1; atomicAdd(Q.rdeg_all + r, 1u); atomicAdd(Q.cdeg_all + c, 1u);
+    } else {
+        base = __shfl_sync(peers, base, leader);
+        const unsigned long long pos = Q.dest_off[dest] + base + __popc(peers & ((1u << lane) - 1));
+        const int rec = Q.weighted ? 3 : 2;
+        Q.sendbuf[pos * rec] = r; Q.sendbuf[pos * rec + 1] = c;
+        if (Q.weighted) Q.sendbuf[pos * rec + 2] = w;
+    }
+}
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_route(IngestParams Q, RmatParams G, const uint32_t* triples, uint64_t first, uint64_t n) {
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    const uint32_t limit = Q.p * Q.th;
+    unsigned long long bad = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool valid = i < n;
+        uint32_t r = 0, c = 0, w = 1;
+        if (valid) {
+            if (G.enabled) rmat_edge(G, first + i, r, c, w);
+            else if (Q.weighted) { r = triples[i * 3]; c = triples[i * 3 + 1]; w = triples[i * 3 + 2]; }
+            else { const uint2 rc = reinterpret_cast<const uint2*>(triples)[i]; r = rc.x; c = rc.y; }
+            if (r >= limit || c >= limit) { bad++; valid = false; }
+        }
+        if (valid && r == c && !Q.self_loops) valid = false;                 // graph.hpp:339-342
+        if (valid && Q.acyclic && c < r) { uint32_t x = r; r = c; c = x; }   // :344-347
+        if (valid && Q.transpose) { uint32_t x = r; r = c; c = x; }          // :349-350
+        route_emit<FILL>(Q, r, c, w, valid);                                 // :352
+        if (!Q.directed) route_emit<FILL>(Q, c, r, w, valid);                // :354-357
+    }
+    if (!FILL && bad) atomicAdd(&Q.counters[2], bad);
 }
 
 template <bool FILL>
@@ -468,8 +523,10 @@ static void build_cf(gt_graph* g) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// `partitioned`: `triples` / the generator range [gen_first, gen_first + ntriples) is THIS RANK'S SHARE of the records.
 static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int weighted, int on_device,
-                       const RmatParams* gen, uint32_t nvertices, const gt_graph_flags* flags, int compression) {
+                       const RmatParams* gen, uint32_t nvertices, const gt_graph_flags* flags, int compression,
+                       int partitioned = 0, uint64_t gen_first = 0) {
     GT_REQUIRE(ctx, "gt_graph_build: ctx is NULL");
     GT_REQUIRE(flags, "gt_graph_build: flags is NULL");
     GT_REQUIRE(compression == GT_TCSC || compression == GT_TCSC_CF, "gt_graph_build: only _TCSC_ / _TCSC_CF_ are GPU formats");
@@ -524,11 +581,12 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     DevBuf<uint32_t> stage;
     if (!gen && !on_device && ntriples) stage.alloc(std::min(CH, ntriples) * rec_words);
 
-    auto run_pass = [&](bool fill) {
+    // one pass over the records: `route` = the partitioned pre-stage (k_route), else the ingest proper (k_ingest)
+    auto run_pass = [&](bool fill, bool route = false) {
         for (uint64_t first = 0; first < ntriples; first += CH) {
             const uint64_t n = std::min(CH, ntriples - first);
             const uint32_t* src = nullptr;
-            if (!gen) {
+            if (!G.enabled) {
                 if (on_device) src = (const uint32_t*) triples + first * rec_words;
                 else {
                     GT_CUDA(cudaMemcpyAsync(stage.p, (const uint32_t*) triples + first * rec_words, n * rec_words * 4, cudaMemcpyHostToDevice, st));
@@ -536,13 +594,79 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
                 }
             }
             const int grid = grid_for(n, 256, ctx->sm_count, 16);
-            if (fill) k_ingest<true><<<grid, 256, 0, st>>>(Q, G, src, first, n);
-            else k_ingest<false><<<grid, 256, 0, st>>>(Q, G, src, first, n);
+            if (route) {
+                if (fill) k_route<true><<<grid, 256, 0, st>>>(Q, G, src, gen_first + first, n);
+                else k_route<false><<<grid, 256, 0, st>>>(Q, G, src, gen_first + first, n);
+            } else {
+                if (fill) k_ingest<true><<<grid, 256, 0, st>>>(Q, G, src, gen_first + first, n);
+                else k_ingest<false><<<grid, 256, 0, st>>>(Q, G, src, gen_first + first, n);
+            }
             ctx->kernel_launches++;
             GT_CUDA(cudaGetLastError());
-            if (!gen && !on_device) GT_CUDA(cudaStreamSynchronize(st));   // stage is reused
+            if (!G.enabled && !on_device) GT_CUDA(cudaStreamSynchronize(st));   // stage is reused
         }
     };
+
+    // ---- partitioned ingest: flags on the share, entries to their owners, marks and degrees all-reduced ---------------
+    DevBuf<uint32_t> routed;                               // the entries this rank owns, {row, col[, w]} records
+    if (partitioned && ctx->nranks > 1) {
+        GT_REQUIRE(ctx->comm, "gt_graph_build_partitioned: the context has no communicator");
+        const int nr = ctx->nranks;
+        DevBuf<int32_t> d_tile_rank; d_tile_rank.alloc(L.tile_rank.size());
+        GT_CUDA(cudaMemcpyAsync(d_tile_rank.p, L.tile_rank.data(), L.tile_rank.size() * 4, cudaMemcpyHostToDevice, st));
+        DevBuf<unsigned long long> dest_count, dest_off, matrix;
+        dest_count.alloc(nr); dest_off.alloc(nr); matrix.alloc((size_t) nr * (nr + 1));
+        GT_CUDA(cudaMemsetAsync(dest_count.p, 0, (size_t) nr * 8, st));
+        Q.tile_rank = d_tile_rank.p; Q.dest_count = dest_count.p; Q.dest_off = dest_off.p;
+        run_pass(false, true);
+        // what every rank sends to every rank (+ its share of the record count), one all-gather
+        std::vector<unsigned long long> h_matrix((size_t) nr * (nr + 1));
+        {
+            unsigned long long* mine = matrix.p + (size_t) ctx->rank * (nr + 1);
+            GT_CUDA(cudaMemcpyAsync(mine, dest_count.p, (size_t) nr * 8, cudaMemcpyDeviceToDevice, st));
+            const unsigned long long share = ntriples;
+            GT_CUDA(cudaMemcpyAsync(mine + nr, &share, 8, cudaMemcpyHostToDevice, st));
+            comm_allgather_inplace(ctx->comm, COMM_WORLD, matrix.p, (size_t) nr + 1, CT_U64, st);
+            GT_CUDA(cudaMemcpyAsync(h_matrix.data(), matrix.p, h_matrix.size() * 8, cudaMemcpyDeviceToHost, st));
+        }
+        // marks, degrees and the bad-record count of the WHOLE list (every rank needs the rows/columns of all its segments)
+        comm_allreduce(ctx->comm, COMM_WORLD, I_all.p, I_all.p, nall, CT_U8, CO_MAX, st);
+        comm_allreduce(ctx->comm, COMM_WORLD, J_all.p, J_all.p, nall, CT_U8, CO_MAX, st);
+        comm_allreduce(ctx->comm, COMM_WORLD, rdeg_all.p, rdeg_all.p, nall, CT_U32, CO_SUM, st);
+        comm_allreduce(ctx->comm, COMM_WORLD, cdeg_all.p, cdeg_all.p, nall, CT_U32, CO_SUM, st);
+        comm_allreduce(ctx->comm, COMM_WORLD, counters.p + 2, counters.p + 2, 1, CT_U64, CO_SUM, st);
+        GT_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint64_t> scount(nr), sdispl(nr), rcount(nr), rdispl(nr);
+        std::vector<unsigned long long> h_off(nr);
+        uint64_t nsend = 0, nrecv = 0, nrecords = 0;
+        const uint64_t rec_bytes = rec_words * 4;
+        for (int q = 0; q < nr; q++) {
+            const uint64_t s_q = h_matrix[(size_t) ctx->rank * (nr + 1) + q], r_q = h_matrix[(size_t) q * (nr + 1) + ctx->rank];
+            h_off[q] = nsend;
+            scount[q] = s_q * rec_bytes; sdispl[q] = nsend * rec_bytes; nsend += s_q;
+            rcount[q] = r_q * rec_bytes; rdispl[q] = nrecv * rec_bytes; nrecv += r_q;
+            nrecords += h_matrix[(size_t) q * (nr + 1) + nr];
+        }
+        g->nedges_input = nrecords;
+        DevBuf<uint32_t> sendbuf; sendbuf.alloc(std::max<uint64_t>(nsend, 1) * rec_words);
+        routed.alloc(std::max<uint64_t>(nrecv, 1) * rec_words);
+        GT_CUDA(cudaMemcpyAsync(dest_off.p, h_off.data(), (size_t) nr * 8, cudaMemcpyHostToDevice, st));
+        GT_CUDA(cudaMemsetAsync(dest_count.p, 0, (size_t) nr * 8, st));
+        Q.sendbuf = sendbuf.p;
+        run_pass(true, true);
+        // own entries stay on the device; the rest travels as one grouped send/recv exchange
+        if (scount[ctx->rank])
+            GT_CUDA(cudaMemcpyAsync((uint8_t*) routed.p + rdispl[ctx->rank], (const uint8_t*) sendbuf.p + sdispl[ctx->rank], scount[ctx->rank], cudaMemcpyDeviceToDevice, st));
+        scount[ctx->rank] = rcount[ctx->rank] = 0;
+        comm_alltoallv_bytes(ctx->comm, (const uint8_t*) sendbuf.p, scount.data(), sdispl.data(), (uint8_t*) routed.p, rcount.data(), rdispl.data(), st);
+        GT_CUDA(cudaStreamSynchronize(st));
+        // from here on: the ordinary build over the routed entries (flags already applied, marks already complete)
+        triples = routed.p; ntriples = nrecv; on_device = 1;
+        G.enabled = 0;
+        Q.self_loops = 1; Q.acyclic = 0; Q.transpose = 0; Q.directed = 1; Q.no_marks = 1;
+        gen_first = 0;
+        stage.release();
+    }
 
     run_pass(false);
     unsigned long long h_counters[4];
@@ -560,6 +684,7 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
     run_pass(true);
     GT_CUDA(cudaStreamSynchronize(st));
     stage.release();
+    routed.release();
 
     // ---- sort (+ dedup) ---------------------------------------------------------------------
     uint64_t* sorted_keys = keys.p;
@@ -813,6 +938,29 @@ extern "C" int gt_graph_build_rmat(gt_ctx* ctx, uint32_t scale, uint64_t nedges,
         GT_REQUIRE(scale >= 1 && scale <= 31, "gt_graph_build_rmat: scale must be in [1, 31]");
         gt::RmatParams P = gt::make_rmat_params(scale, seed, weighted);
         *out = gt::build(ctx, nullptr, nedges, weighted, 1, &P, 1u << scale, flags, compression);
+    });
+}
+
+// Partitioned ingest: every rank passes ITS SHARE of the records (Graph::parread_binary reads 1/p of the file per rank,
+// src/mat/graph.hpp:307-335) and the entries travel to the owners of their tiles (Matrix::distribute, matrix.hpp:692-810).
+extern "C" int gt_graph_build_partitioned(gt_ctx* ctx, const void* share, uint64_t nshare, int weighted, int on_device,
+                                          uint32_t nvertices, const gt_graph_flags* flags, int compression, gt_graph** out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(out, "gt_graph_build_partitioned: out is NULL");
+        *out = gt::build(ctx, share, nshare, weighted, on_device, nullptr, nvertices, flags, compression, 1);
+    });
+}
+
+extern "C" int gt_graph_build_rmat_partitioned(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uint64_t seed, int weighted,
+                                               const gt_graph_flags* flags, int compression, gt_graph** out) {
+    return gt::guarded([&] {
+        GT_REQUIRE(out && ctx, "gt_graph_build_rmat_partitioned: NULL argument");
+        GT_REQUIRE(scale >= 1 && scale <= 31, "gt_graph_build_rmat_partitioned: scale must be in [1, 31]");
+        gt::RmatParams P = gt::make_rmat_params(scale, seed, weighted);
+        // rank r generates records [r * (nedges / p), ...) and the last rank the remainder: the reference's split of the file
+        const uint64_t share = nedges / (uint64_t) ctx->nranks, first = share * (uint64_t) ctx->rank;
+        const uint64_t n = ctx->rank == ctx->nranks - 1 ? nedges - first : share;
+        *out = gt::build(ctx, nullptr, n, weighted, 1, &P, 1u << scale, flags, compression, 1, first);
     });
 }
 

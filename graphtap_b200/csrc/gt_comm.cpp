@@ -39,6 +39,8 @@ struct Nccl {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,6 +69,8 @@ static Nccl& nccl() {
     n.AllReduce = (decltype(n.AllReduce)) sym("ncclAllReduce");
     n.AllGather = (decltype(n.AllGather)) sym("ncclAllGather");
     n.ReduceScatter = (decltype(n.ReduceScatter)) sym("ncclReduceScatter");
+    n.Send = (decltype(n.Send)) sym("ncclSend");
+    n.Recv = (decltype(n.Recv)) sym("ncclRecv");
     n.GroupStart = (decltype(n.GroupStart)) sym("ncclGroupStart");
     n.GroupEnd = (decltype(n.GroupEnd)) sym("ncclGroupEnd");
     n.GetErrorString = (decltype(n.GetErrorString)) sym("ncclGetErrorString");
@@ -152,6 +156,17 @@ void comm_allgather_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommT
 void comm_reduce_scatter_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, CommOp op, cudaStream_t s) {
     const size_t es = t == CT_F64 || t == CT_U64 ? 8 : t == CT_U32 ? 4 : 1;
     GT_NCCL(nccl().ReduceScatter(buf, (char*) buf + (size_t) comm_rank_in(c, g) * count * es, count, nccl_type(t), nccl_op(op), pick(c, g), s));
+}
+// world all-to-all-v of raw bytes: rank r sends send[sdispl[q] .. + scount[q]) to rank q and receives rcount[q] bytes from q
+// at recv[rdispl[q]] (the reference's pairwise Sendrecv redistribution, src/mat/matrix.hpp:692-810, as one grouped exchange)
+void comm_alltoallv_bytes(Comm* c, const uint8_t* send, const uint64_t* scount, const uint64_t* sdispl, uint8_t* recv, const uint64_t* rcount,
+                          const uint64_t* rdispl, cudaStream_t s) {
+    GT_NCCL(nccl().GroupStart());
+    for (int q = 0; q < c->nranks; q++) {
+        if (scount[q]) GT_NCCL(nccl().Send(send + sdispl[q], scount[q], NCCL_UINT8, q, c->world, s));
+        if (rcount[q]) GT_NCCL(nccl().Recv(recv + rdispl[q], rcount[q], NCCL_UINT8, q, c->world, s));
+    }
+    GT_NCCL(nccl().GroupEnd());
 }
 void comm_allreduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, cudaStream_t s) {
     GT_NCCL(nccl().AllReduce(send, recv, count, nccl_type(t), nccl_op(op), pick(c, g), s));

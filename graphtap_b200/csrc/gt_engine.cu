@@ -340,6 +340,9 @@ static void pull_alloc(gt_program* P) {
 static void prog_initialize(gt_program* P) {
     gt_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->stream;
+    const auto t_init = std::chrono::steady_clock::now();     // init_time of -DTIMING (:445-470)
+    struct InitClock { gt_program* P; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+        ~InitClock() { cudaStreamSynchronize(st); P->init_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } } init_clock{P, st, t_init};
     k_init_state<<<grid_for(P->th, 256, ctx->sm_count), 256, 0, st>>>(P->vs(), P->app, P->th, P->vid0, P->prm.root, P->prm.alpha, P->stationary);
     ctx->kernel_launches++;
     if (!P->stationary) ns_initialize(P);       // Y starts at infinity() (:625-635)
@@ -766,6 +769,7 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
         const uint32_t it0 = p->iteration;
         GT_CUDA(cudaEventRecord(p->ev0, ctx->stream));
         p->tm.scatter_gather_ms = p->tm.combine_ms = p->tm.apply_ms = 0;
+        for (auto& v : p->phase_samples) v.clear();
         if (!p->stationary) {
             p->timeline_on = getenv("GT_TIMELINE") != nullptr;
             gt::ns_execute(p, num_iterations);            // records ev1, drains the stream
@@ -777,20 +781,22 @@ extern "C" int gt_program_execute(gt_program* p, uint32_t num_iterations, uint32
             if (peer_used) gt::peer_fence_world(ctx, ctx->stream);
             // -DTIMING counters of the reference (:640-684,1018-1054,1611-1637): wall clock around each phase with
             // the stream drained, only when the "timing" knob is on (it serialises host and device)
-            auto phase = [&](double& acc, auto&& fn) {
+            auto phase = [&](int which, double& acc, auto&& fn) {
                 if (!p->timing) { fn(); return; }
                 GT_CUDA(cudaStreamSynchronize(ctx->stream));
                 const auto t0 = std::chrono::steady_clock::now();
                 fn();
                 GT_CUDA(cudaStreamSynchronize(ctx->stream));
-                acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                acc += ms;
+                p->add_sample(which, p->iteration - it0, ms);
             };
             p->timeline_on = p->pull && getenv("GT_TIMELINE") != nullptr;
             while (true) {
-                phase(p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
-                phase(p->tm.combine_ms, [&] { gt::combine(p); });
+                phase(0, p->tm.scatter_gather_ms, [&] { gt::scatter_gather(p); });
+                phase(1, p->tm.combine_ms, [&] { gt::combine(p); });
                 p->tm.bytes_algorithmic += gt::algorithmic_bytes_iteration(p, gt::cf_first(p), gt::cf_last(p), false);
-                phase(p->tm.apply_ms, [&] { gt::apply(p, check); });
+                phase(2, p->tm.apply_ms, [&] { gt::apply(p, check); });
                 gt::tl_mark(p, "applied", ctx->stream);
                 p->iteration++;
                 if (check) {
@@ -926,6 +932,17 @@ extern "C" int gt_program_checksum(gt_program* p, uint64_t* value_sum, uint64_t*
         }
         if (value_sum) *value_sum = sum;
         if (reachable) *reachable = cnt;
+    });
+}
+
+extern "C" int gt_program_timing_samples(gt_program* p, int phase, double* out_ms, uint32_t cap, uint32_t* n) {
+    return gt::guarded([&] {
+        GT_REQUIRE(p && n, "gt_program_timing_samples: NULL argument");
+        GT_REQUIRE(phase >= 0 && phase <= 3, "gt_program_timing_samples: phase must be 0 (scatter_gather), 1 (combine), 2 (apply) or 3 (init)");
+        if (phase == 3) { *n = 1; if (out_ms && cap) out_ms[0] = p->init_ms; return; }
+        const std::vector<double>& v = p->phase_samples[phase];
+        *n = (uint32_t) v.size();
+        for (uint32_t i = 0; out_ms && i < cap && i < v.size(); i++) out_ms[i] = v[i];
     });
 }
 

@@ -120,6 +120,8 @@ void comm_reduce(Comm* c, CommGroup g, const void* send, void* recv, size_t coun
 void comm_allgather_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, cudaStream_t s);
 void comm_reduce_scatter_inplace(Comm* c, CommGroup g, void* buf, size_t count, CommType t, CommOp op, cudaStream_t s);
 void comm_allreduce(Comm* c, CommGroup g, const void* send, void* recv, size_t count, CommType t, CommOp op, cudaStream_t s);
+void comm_alltoallv_bytes(Comm* c, const uint8_t* send, const uint64_t* scount, const uint64_t* sdispl, uint8_t* recv, const uint64_t* rcount,
+                          const uint64_t* rdispl, cudaStream_t s);
 
 }  // namespace gt
 

@@ -149,6 +149,9 @@ spmv_push_chunks(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ I
                 if (SKIP_INF && SR::skip(xv)) continue;
                 const T val = WEIGHTED ? SR::mul(xv, wts[k]) : xv;
                 if constexpr (IMPROVED) {
+                    // the filter read goes to L2, one per edge, in line: through L1 (stale lines are safe, y never increases)
+                    // and / or with a thread's four reads issued ahead of its REDs it measured 2-7 % slower
+                    // (profiles/r02_ns_filter_read_variants.md)
                     if (t) { if (val < __ldcg(y + rows[k]) && val < atomicMin(y + rows[k], val)) t[rows[k]] = 1; }
                     else SR::reduce_dense(y + rows[k], val);
                 } else {

@@ -84,6 +84,8 @@ struct NsState {
     uint32_t x_epoch = 0, y_epoch = 0;
     int active_slot = 0;                         // d_active slot of the iteration being enqueued
     bool any_heavy = false, bottom_up_ok = false, nccl_exchange = false;
+    bool publish_via_put = false;                // this execute(): the convergence count of iteration n is written to the host by iteration n + 1's put kernel
+    bool publish_prev = false;                   // ... and the iteration being enqueued has a predecessor in this execute()
     cudaEvent_t ev_it[2] = {nullptr, nullptr};
     unsigned long long* h_stats = nullptr;       // pinned
 };
@@ -162,7 +164,8 @@ __device__ __forceinline__ uint32_t ns_mode(unsigned k, uint32_t n, unsigned lon
 __global__ void __launch_bounds__(256) k_ns_put_x(const uint32_t* __restrict__ dense, const uint32_t* __restrict__ xi, const uint32_t* __restrict__ xv,
                                                    unsigned int* __restrict__ count, uint32_t n, unsigned long long* __restrict__ frontier_edges,
                                                    NsRule rule, uint32_t* own_hdr, PutTargets T, uint32_t epoch, unsigned int* done,
-                                                   unsigned long long* __restrict__ next_active) {
+                                                   unsigned long long* __restrict__ next_active, const unsigned long long* __restrict__ prev_active,
+                                                   volatile unsigned long long* host_prev) {
     const unsigned k = *count;
     const uint32_t mode = ns_mode(k, n, *frontier_edges, rule);
     // only as many CTAs as the payload can keep busy take part (32 KB each): with a frontier of a few hundred columns the
@@ -185,6 +188,9 @@ __global__ void __launch_bounds__(256) k_ns_put_x(const uint32_t* __restrict__ d
     if (threadIdx.x == 0) {
         own_hdr[0] = mode; own_hdr[1] = k; *done = 0;
         *count = 0; *frontier_edges = 0; *next_active = 0;      // what this iteration's applicator accumulates into
+        // the (all-reduced) active count of the previous iteration goes straight to the pinned host word the convergence
+        // check reads: no device-to-host copy sits between an iteration's all-reduce and the next iteration's first kernel
+        if (host_prev) { *host_prev = *prev_active; __threadfence_system(); }
     }
     if ((int) threadIdx.x < T.n) {
         volatile uint32_t* h = T.hdr[threadIdx.x];
@@ -339,21 +345,34 @@ __global__ void __launch_bounds__(1024) k_ns_pack_y(const NsYSend* __restrict__ 
     typedef cub::BlockScan<unsigned, 1024> BS;
     __shared__ typename BS::TempStorage tmp;
     __shared__ unsigned base_s;
-    const uint32_t per_iter = 1024 * 4;
+    // 16 flags per thread and round (four independent 4-byte loads in flight); a round without any flag — most of them in
+    // the long tail of small iterations — costs one barrier and no scan
+    const uint32_t per_iter = 1024 * 16;
     for (uint32_t start = blockIdx.x * per_iter; start < Q.n; start += gridDim.x * per_iter) {
-        const uint32_t i0 = start + threadIdx.x * 4;              // n is padded to a multiple of 4 flags
-        const uint32_t f4 = (i0 < Q.n) ? *reinterpret_cast<const uint32_t*>(Q.t + i0) : 0u;
-        const unsigned mine = __popc(f4 & 0x01010101u);
+        uint32_t f4[4];
+        unsigned mine = 0;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t i0 = start + w * 4096 + threadIdx.x * 4;      // n is padded to a multiple of 4 flags
+            f4[w] = (i0 < Q.n) ? *reinterpret_cast<const uint32_t*>(Q.t + i0) : 0u;
+            mine += __popc(f4[w] & 0x01010101u);
+        }
+        if (!__syncthreads_or(mine != 0)) continue;
         unsigned off, total;
         BS(tmp).ExclusiveSum(mine, off, total);
-        if (threadIdx.x == 0 && total) base_s = atomicAdd(Q.count, total);
+        if (threadIdx.x == 0) base_s = atomicAdd(Q.count, total);
         __syncthreads();
         if (mine) {
             unsigned pos = base_s + off;
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if ((f4 >> (8 * u)) & 1u) { Q.yi[pos] = i0 + u; Q.yv[pos] = Q.y[i0 + u]; pos++; }
-            *reinterpret_cast<uint32_t*>(Q.t + i0) = 0u;          // cleared for the next iteration (:1795-1801)
+            for (int w = 0; w < 4; w++) {
+                if (!f4[w]) continue;
+                const uint32_t i0 = start + w * 4096 + threadIdx.x * 4;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if ((f4[w] >> (8 * u)) & 1u) { Q.yi[pos] = i0 + u; Q.yv[pos] = Q.y[i0 + u]; pos++; }
+                *reinterpret_cast<uint32_t*>(Q.t + i0) = 0u;      // cleared for the next iteration (:1795-1801)
+            }
         }
         __syncthreads();
     }
@@ -674,9 +693,12 @@ static void ns_exchange_x(gt_program* P) {
         }
     }
     N.x_epoch++;
+    const int prev = N.active_slot ^ 1;
     k_ns_put_x<<<T.n ? 2 * ctx->sm_count : 1, 256, 0, st>>>(N.x[k], N.xi[k], N.xv[k], N.counters.p + 1, own.nnz, N.stats.p + 3, rule, own_hdr, T,
-                                                            N.x_epoch, N.counters.p + 2, P->d_active.p + N.active_slot);
+                                                            N.x_epoch, N.counters.p + 2, P->d_active.p + N.active_slot,
+                                                            N.publish_prev ? P->d_active.p + prev : nullptr, N.publish_prev ? P->h_active + prev : nullptr);
     ctx->kernel_launches++;
+    if (N.publish_prev) GT_CUDA(cudaEventRecord(N.ev_it[prev], st));
     tl_mark(P, "x_put", st);
     if (N.wx) { peer_wait_all(ctx, N.wx, N.x_epoch, st); tl_mark(P, "x_arrived", st); }
     GT_CUDA(cudaGetLastError());
@@ -719,7 +741,7 @@ static void ns_combine(gt_program* P) {
     tl_mark(P, "tiles_done", st);
     if (N.wy) {
         N.y_epoch++;
-        const dim3 gp(std::max(1, std::min<int>(ctx->sm_count, (int) ((N.ychunk + 4095) / 4096))), N.nsend);
+        const dim3 gp(std::max(1, std::min<int>(ctx->sm_count, (int) ((N.ychunk + 16383) / 16384))), N.nsend);
         k_ns_pack_y<<<gp, 1024, 0, st>>>(N.ysend.p);
         k_ns_put_y<<<dim3(ctx->sm_count, N.nsend), 256, 0, st>>>(N.ysend.p, P->activity_filtering_ratio, N.y_epoch);
         tl_mark(P, "y_put", st);
@@ -755,8 +777,10 @@ static void ns_apply(gt_program* P, uint32_t iteration, int slot) {
     // has_converged (:1884-1923): the world all-reduce is also the ordering point that lets the windows have one buffer
     tl_mark(P, "applied", st);
     if (ctx->comm) { comm_allreduce(ctx->comm, COMM_WORLD, P->d_active.p + slot, P->d_active.p + slot, 1, CT_U64, CO_SUM, st); tl_mark(P, "allreduced", st); }
-    GT_CUDA(cudaMemcpyAsync(P->h_active + slot, P->d_active.p + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    GT_CUDA(cudaEventRecord(N.ev_it[slot], st));
+    if (!N.publish_via_put) {         // otherwise the next iteration's put kernel hands the count to the host (k_ns_put_x)
+        GT_CUDA(cudaMemcpyAsync(P->h_active + slot, P->d_active.p + slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        GT_CUDA(cudaEventRecord(N.ev_it[slot], st));
+    }
     GT_CUDA(cudaGetLastError());
 }
 
@@ -779,24 +803,32 @@ void ns_execute(gt_program* P, uint32_t num_iterations) {
     cudaStream_t st = ctx->stream;
     const bool check = num_iterations == 0;
     const bool peer = N.wx || N.wy;
-    auto timed = [&](double& acc, auto&& fn) {
+    uint32_t sample_it = 0;                              // iteration (from 0) the -DTIMING sample belongs to
+    auto timed = [&](int which, double& acc, auto&& fn) {
         if (!P->timing) { fn(); return; }
         GT_CUDA(cudaStreamSynchronize(st));
         const auto t0 = std::chrono::steady_clock::now();
         fn();
         GT_CUDA(cudaStreamSynchronize(st));
-        acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        acc += ms;
+        P->add_sample(which, sample_it, ms);
     };
     GT_CUDA(cudaMemsetAsync(N.stats.p, 0, 3 * sizeof(unsigned long long), st));
     if (peer) peer_fence_world(ctx, st);                 // every rank has left whatever used the windows before (run_phase, an earlier execute)
-    timed(P->tm.scatter_gather_ms, [&] { ns_x_from_state(P); });
+    timed(0, P->tm.scatter_gather_ms, [&] { ns_x_from_state(P); });
     const uint32_t it0 = P->iteration;
+    // run-ahead convergence mode: iteration n + 1 is always enqueued before the count of iteration n is read, so its put
+    // kernel can deliver that count (fixed-iteration runs never read it; the timing knob serialises and keeps the copy)
+    N.publish_via_put = check && !P->timing && !N.nccl_exchange;
     auto enqueue = [&](uint32_t n) {                     // iteration it0 + n
         P->iteration = it0 + n;
+        sample_it = n;
         N.active_slot = (int) (n & 1);
-        timed(P->tm.scatter_gather_ms, [&] { ns_exchange_x(P); });
-        timed(P->tm.combine_ms, [&] { ns_combine(P); });
-        timed(P->tm.apply_ms, [&] { ns_apply(P, it0 + n, (int) (n & 1)); });
+        N.publish_prev = N.publish_via_put && n > 0;
+        timed(0, P->tm.scatter_gather_ms, [&] { ns_exchange_x(P); });
+        timed(1, P->tm.combine_ms, [&] { ns_combine(P); });
+        timed(2, P->tm.apply_ms, [&] { ns_apply(P, it0 + n, (int) (n & 1)); });
     };
     // vertex-phase bytes per iteration: JC + state for the messenger, IR + y + state for the applicator
     const uint64_t vertex_bytes = 8ull * (*P->pcol)[P->own_col_slot].nnz + 16ull * (*P->prow)[P->own_row_slot].nnz;
@@ -819,6 +851,7 @@ void ns_execute(gt_program* P, uint32_t num_iterations) {
         }
     }
     P->iteration = it0 + done;
+    N.publish_via_put = N.publish_prev = false;
     GT_CUDA(cudaMemcpyAsync(N.h_stats, N.stats.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (peer) GT_CUDA(cudaMemcpyAsync(&P->h_active[2], peer_error_word(ctx), 4, cudaMemcpyDeviceToHost, st));
     GT_CUDA(cudaEventRecord(P->ev1, st));
@@ -833,6 +866,7 @@ void ns_run_phase(gt_program* P, int phase) {
     gt_ctx* ctx = P->ctx;
     NsState& N = *P->ns;
     N.active_slot = 0;
+    N.publish_via_put = N.publish_prev = false;
     if (phase == 0) {
         if (N.wx || N.wy) peer_fence_world(ctx, ctx->stream);
         ns_x_from_state(P);

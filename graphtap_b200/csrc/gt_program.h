@@ -96,6 +96,15 @@ struct gt_program {
     double bfs_bottom_up_ratio = 0.05;            // BFS on an undirected single-GPU graph: bottom-up pass above this frontier share (0 = never)
     bool timing = false;
     gt_timing tm{};
+    // -DTIMING vectors of the reference (:202-208): one wall-clock sample per iteration and phase of the latest execute()
+    // (0 scatter_gather, 1 combine, 2 apply), and init_time; filled only while the "timing" knob is on
+    std::vector<double> phase_samples[3];
+    double init_ms = 0;
+    void add_sample(int phase, uint32_t it, double ms) {
+        std::vector<double>& v = phase_samples[phase];
+        if (v.size() <= it) v.resize((size_t) it + 1, 0.0);
+        v[it] += ms;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     gt::VState vs() { return gt::VState{rank.p, a.p, b.p, C.p}; }

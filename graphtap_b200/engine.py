@@ -131,6 +131,31 @@ def read_edge_list(path: str, weighted: bool) -> np.ndarray:
     return np.asarray(rows, dtype="<u4").reshape(-1, rec)
 
 
+def share_of_file(filesize: int, rec_bytes: int, rank: int, nranks: int) -> tuple[int, int]:
+    """Byte range [offset, endpos) of a binary edge file that ``rank`` reads, exactly ``Graph::parread_binary``'s split
+    (``src/mat/graph.hpp:317-323``): equal whole-record shares, the last rank also takes the remainder."""
+    share = (filesize // nranks) // rec_bytes * rec_bytes
+    offset = share * rank
+    endpos = filesize if rank == nranks - 1 else offset + share
+    return offset, endpos
+
+
+def read_edge_list_share(path: str, weighted: bool, rank: int, nranks: int) -> np.ndarray:
+    """This rank's share of the records.  Binary files: only the share's bytes are read from disk.  Text files: the
+    reference splits at byte offsets and re-synchronises on line ends (``src/mat/graph.hpp:194-304``); here every rank
+    parses the file and keeps the records whose index falls in its equal share (same union, simpler)."""
+    rec = 3 if weighted else 2
+    if not _looks_like_text(path):
+        size = os.path.getsize(path)
+        if size % (rec * 4):
+            raise capi.GraphTapError(capi.GT_ERR_INVALID, f"{path}: size is not a multiple of the {rec * 4}-byte record")
+        offset, endpos = share_of_file(size, rec * 4, rank, nranks)
+        return np.fromfile(path, dtype="<u4", count=(endpos - offset) // 4, offset=offset).reshape(-1, rec)
+    allrec = read_edge_list(path, weighted)
+    share = allrec.shape[0] // nranks
+    return allrec[share * rank: allrec.shape[0] if rank == nranks - 1 else share * (rank + 1)]
+
+
 class Graph:
     """``Graph<Weight, Integer_Type, Fractional_Type>`` (``src/mat/graph.hpp:33-67``)."""
 
@@ -142,38 +167,50 @@ class Graph:
         return capi.GraphFlags(int(directed), int(transpose), int(self_loops), int(acyclic), int(parallel_edges))
 
     def load(self, filepath, nrows, ncols, directed=True, transpose=False, self_loops=True, acyclic=False,
-             parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_):
+             parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_, partitioned=None):
         """``Graph::load`` (``src/mat/graph.hpp:104-148``): sniffs the file type (the reference shells out to
-        file(1): "ASCII" -> text, "data" -> binary) and reads the whole edge list; every rank builds its own
-        tiles from it (gt_graph_build)."""
-        triples = read_edge_list(filepath, self.weighted)
-        return self.load_triples(triples, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling_type, compression_type)
+        file(1): "ASCII" -> text, "data" -> binary).  With several ranks every rank reads ITS SHARE of the file and the
+        entries are redistributed on the device (gt_graph_build_partitioned — the reference's parread + distribute);
+        ``partitioned=False`` makes every rank read the whole list and keep its own tiles (gt_graph_build)."""
+        Env.init()
+        if partitioned is None:
+            partitioned = Env.nranks > 1
+        if partitioned:
+            triples = read_edge_list_share(filepath, self.weighted, Env.rank, Env.nranks)
+        else:
+            triples = read_edge_list(filepath, self.weighted)
+        return self.load_triples(triples, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling_type, compression_type,
+                                 partitioned=partitioned)
 
     load_binary = load
     load_text = load
 
     def load_triples(self, triples: np.ndarray, nvertices, directed=True, transpose=False, self_loops=True, acyclic=False,
-                     parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_):
+                     parallel_edges=True, tiling_type=_2DT_, compression_type=_TCSC_, partitioned=False):
+        """``triples``: the global record list, or — ``partitioned`` — this rank's share of it."""
         if tiling_type != _2DT_:
             raise capi.GraphTapError(capi.GT_ERR_UNSUPPORTED, "only _2DT_ tiling is provided (every reference app uses it)")
         Env.init()
         triples = np.ascontiguousarray(triples, dtype="<u4")
         fl = self._flags(directed, transpose, self_loops, acyclic, parallel_edges)
         h = C.c_void_p()
-        check(lib().gt_graph_build(Env.ctx, triples.ctypes.data_as(C.c_void_p), triples.shape[0], int(self.weighted), 0,
-                                   int(nvertices), C.byref(fl), int(compression_type), C.byref(h)))
+        build = lib().gt_graph_build_partitioned if partitioned else lib().gt_graph_build
+        check(build(Env.ctx, triples.ctypes.data_as(C.c_void_p), triples.shape[0], int(self.weighted), 0,
+                    int(nvertices), C.byref(fl), int(compression_type), C.byref(h)))
         self.handle = h
         return self
 
     def load_rmat(self, scale, nedges=None, seed=None, directed=True, transpose=False, self_loops=True, acyclic=False,
-                  parallel_edges=True, compression_type=_TCSC_):
-        """Synthetic RMAT input generated on the device (bench tooling; same stream as graphtap_b200.rmat)."""
+                  parallel_edges=True, compression_type=_TCSC_, partitioned=False):
+        """Synthetic RMAT input generated on the device (bench tooling; same stream as graphtap_b200.rmat).
+        ``partitioned``: every rank generates 1/p of the records and routes them to the tile owners."""
         Env.init()
         fl = self._flags(directed, transpose, self_loops, acyclic, parallel_edges)
         h = C.c_void_p()
-        check(lib().gt_graph_build_rmat(Env.ctx, scale, (16 << scale) if nedges is None else nedges,
-                                        scale if seed is None else seed, int(self.weighted), C.byref(fl),
-                                        int(compression_type), C.byref(h)))
+        build = lib().gt_graph_build_rmat_partitioned if partitioned else lib().gt_graph_build_rmat
+        check(build(Env.ctx, scale, (16 << scale) if nedges is None else nedges,
+                    scale if seed is None else seed, int(self.weighted), C.byref(fl),
+                    int(compression_type), C.byref(h)))
         self.handle = h
         return self
 

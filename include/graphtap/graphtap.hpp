@@ -132,16 +132,22 @@ class Graph {
         else load_binary(filepath, nrows, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
         Env::print_time("Ingress", Env::clock() - t1);
     }
+    // Graph::parread_binary (src/mat/graph.hpp:307-372): every rank reads its share of the file — equal whole-record shares,
+    // the last rank also the remainder (:317-323) — and the library redistributes the entries (gt_graph_build_partitioned).
     void load_binary(std::string filepath, Integer_Type nrows, Integer_Type, bool directed, bool transpose, bool self_loops, bool acyclic,
                      bool parallel_edges, Tiling_type tiling, Compression_type compression) {
         std::ifstream fin(filepath.c_str(), std::ios_base::binary);
         if (!fin.is_open()) { fprintf(stderr, "Unable to open input file\n"); Env::exit(1); }
         fin.seekg(0, std::ios_base::end);
-        const uint64_t bytes = (uint64_t) fin.tellg(), rec = weighted ? 12 : 8;
-        std::vector<uint32_t> triples(bytes / 4);
-        fin.seekg(0, std::ios_base::beg);
-        fin.read((char*) triples.data(), (std::streamsize) (bytes / rec * rec));
-        build(filepath, triples, bytes / rec, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression);
+        const uint64_t filesize = (uint64_t) fin.tellg(), rec = weighted ? 12 : 8;
+        const uint64_t share = (filesize / (uint64_t) Env::nranks) / rec * rec;
+        const uint64_t offset = share * (uint64_t) Env::rank;
+        const uint64_t endpos = Env::rank == Env::nranks - 1 ? filesize / rec * rec : offset + share;
+        std::vector<uint32_t> triples((endpos - offset) / 4);
+        fin.seekg((std::streamoff) offset, std::ios_base::beg);
+        fin.read((char*) triples.data(), (std::streamsize) (endpos - offset));
+        if ((uint64_t) fin.gcount() != endpos - offset) { fprintf(stderr, "read() failure\n"); Env::exit(1); }
+        build(filepath, triples, (endpos - offset) / rec, nrows, directed, transpose, self_loops, acyclic, parallel_edges, tiling, compression, true);
     }
     // text edge lists (src/mat/graph.hpp:194-304): '#'/'%' header lines, then "row col[ weight]" per line
     void load_text(std::string filepath, Integer_Type nrows, Integer_Type, bool directed, bool transpose, bool self_loops, bool acyclic,
@@ -174,16 +180,20 @@ class Graph {
         }
         return n > 0;
     }
+    // `share`: `triples` is this rank's share of the records (binary files); else every rank holds the whole list (text files)
     void build(const std::string& filepath, std::vector<uint32_t>& triples, uint64_t n, Integer_Type nrows, bool directed, bool transpose,
-               bool self_loops, bool acyclic, bool parallel_edges, Tiling_type tiling, Compression_type compression) {
+               bool self_loops, bool acyclic, bool parallel_edges, Tiling_type tiling, Compression_type compression, bool share = false) {
         if (tiling != _2DT_ || (compression != _TCSC_ && compression != _TCSC_CF_)) {
             fprintf(stderr, "graphtap_b200: only _2DT_ tiling with _TCSC_/_TCSC_CF_ compression runs on the device\n");
             Env::exit(1);
         }
         gt_graph_flags fl = {directed, transpose, self_loops, acyclic, parallel_edges};
-        if (gt_graph_build(Env::ctx, triples.data(), n, weighted, 0, nrows, &fl, compression == _TCSC_ ? GT_TCSC : GT_TCSC_CF, &handle))
+        if ((share ? gt_graph_build_partitioned : gt_graph_build)(Env::ctx, triples.data(), n, weighted, 0, nrows, &fl,
+                                                                  compression == _TCSC_ ? GT_TCSC : GT_TCSC_CF, &handle))
             Env::fail("gt_graph_build");
-        if (Env::is_master) printf("\n%s: Read %lu edges\n", filepath.c_str(), (unsigned long) n);
+        gt_graph_info gi;
+        gt_graph_info_get(handle, &gi);
+        if (Env::is_master) printf("\n%s: Read %lu edges\n", filepath.c_str(), (unsigned long) gi.nedges_input);
     }
   public:
     void free() { if (handle) { gt_graph_free(handle); handle = nullptr; } }
@@ -247,6 +257,7 @@ class Vertex_Program {
     bool stationary, gather_depends_on_apply, apply_depends_on_iter;
     std::vector<Vertex_State> V;            // refreshed from the device after execute()/initialize()
     bool materialize_V = true;              // set false to skip the device->host copy of V after execute()
+    double execute_ms = 0;                  // execute_time of the latest execute() (-DTIMING, :436-438)
     gt_program* handle = nullptr;
 
     void execute(Integer_Type num_iterations_ = 0) {
@@ -254,9 +265,13 @@ class Vertex_Program {
         ensure();
         uint32_t done = 0;
         if (gt_program_execute(handle, num_iterations_, &done)) Env::fail("gt_program_execute");
+        // the reference prints one "Iteration:" line per pass of the loop (:431); the device runs the iterations without
+        // a host round trip, so the lines of this execute() come out together, before "Execute time"
+        for (Integer_Type it = iteration + 1; it <= (Integer_Type) done; it++) Env::print_num("Iteration: ", it);
         iteration = done;
         gt_timing tm;
         gt_program_timing(handle, &tm);
+        execute_ms = tm.execute_ms;
         Env::print_time("Execute", tm.execute_ms * 1e-3);
         if (materialize_V) pull_states();
     }
@@ -277,7 +292,32 @@ class Vertex_Program {
     }
     void display(Integer_Type count = 31) {
         if (V.empty()) pull_states();
+        Env::barrier();
         if (Env::rank) return;
+#ifdef TIMING
+        {   // the -DTIMING report (src/vp/vertex_program.hpp:2134-2152), all in ms
+            double init = 0, st[3][3];
+            uint32_t n = 0;
+            gt_program_timing_samples(handle, 3, &init, 1, &n);
+            for (int ph = 0; ph < 3; ph++) {
+                gt_program_timing_samples(handle, ph, nullptr, 0, &n);
+                std::vector<double> v(n);
+                if (n) gt_program_timing_samples(handle, ph, v.data(), n, &n);
+                double sum = 0, sq = 0;
+                for (double x : v) { sum += x; sq += x * x; }
+                const double mean = sum / v.size();
+                st[ph][0] = sum; st[ph][1] = mean; st[ph][2] = std::sqrt(sq / v.size() - mean * mean);     // stats(), :2184-2190
+            }
+            std::cout << "Init           time: " << init << " ms" << std::endl;
+            const char* names[3] = {"Scatter_gather", "Combine       ", "Apply         "};
+            for (int ph = 0; ph < 3; ph++)
+                std::cout << names[ph] << " time (sum: avg +/- std_dev): " << st[ph][0] << ": " << st[ph][1] << " +/- " << st[ph][2] << " ms" << std::endl;
+            std::cout << "Execute        time: " << execute_ms << " ms" << std::endl;
+            std::cout << "TIMING " << init;
+            for (int ph = 0; ph < 3; ph++) std::cout << " " << st[ph][0] << " " << st[ph][1] << " " << st[ph][2];
+            std::cout << " " << execute_ms << std::endl;
+        }
+#endif
         gt_graph_info gi;
         gt_graph_info_get(graph->handle, &gi);
         const uint64_t base = (uint64_t) gi.layout.owned_segment * gi.layout.tile_height;
@@ -294,6 +334,9 @@ class Vertex_Program {
             if (gt_program_create(graph->handle, gt_app_of<Vertex_State>::value, stationary, gather_depends_on_apply, apply_depends_on_iter,
                                   ordering == _ROW_ ? GT_ROW : GT_COL, &prm, &handle))
                 Env::fail("gt_program_create");
+#ifdef TIMING
+            if (gt_program_set(handle, "timing", 1.0)) Env::fail("gt_program_set");     // per-phase wall clocks, as the reference's -DTIMING build
+#endif
         }
         return handle;
     }

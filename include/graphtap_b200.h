@@ -133,8 +133,9 @@ typedef struct {
 
 /* `triples` is the reference's on-disk record array (src/ds/triple.hpp:9-18,40-49):
  * {u32 row, u32 col} or, weighted, {u32 row, u32 col, u32 w}.  It is the GLOBAL edge list: every rank
- * passes the same records (or generates them) and keeps the tiles it owns, which replaces the
- * reference's read-a-share-then-Sendrecv `distribute` (src/mat/matrix.hpp:692-810) with no exchange.
+ * passes the same records (or generates them) and keeps the tiles it owns — no exchange, the cheap way for
+ * generated graphs; gt_graph_build_partitioned below is the reference's read-a-share-then-redistribute
+ * (src/mat/matrix.hpp:692-810).
  * `on_device` != 0: `triples` is a device pointer (already resident in HBM). */
 GT_API int gt_graph_build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int weighted, int on_device,
                    uint32_t nvertices, const gt_graph_flags* flags, int compression, gt_graph** out);
@@ -142,6 +143,19 @@ GT_API int gt_graph_build(gt_ctx* ctx, const void* triples, uint64_t ntriples, i
  * Graph500 a,b,c,d, label permutation, weights in [1,128]).  Bench tooling: the reference ships no
  * generator. */
 GT_API int gt_graph_build_rmat(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uint64_t seed, int weighted,
+                        const gt_graph_flags* flags, int compression, gt_graph** out);
+/* Partitioned ingest = the reference's own scheme: every rank passes ITS SHARE of the records (Graph::parread_binary reads
+ * bytes [rank*share, ...) of the file, src/mat/graph.hpp:307-335), the per-edge flags run on the share and every entry
+ * travels to the rank that owns its tile (Matrix::distribute's pairwise Sendrecv, src/mat/matrix.hpp:692-810, as one
+ * grouped NCCL send/recv exchange); the non-empty row/column marks and degrees are all-reduced (the reference OR-reduces
+ * them along the row/column groups, :973-1083).  Any split of the global list gives the same graph as gt_graph_build on
+ * the whole list: tiles, maps and orders are bit-identical.  Collective over the context's ranks; with one rank it is
+ * gt_graph_build.  nedges_input of the result = records over all shares. */
+GT_API int gt_graph_build_partitioned(gt_ctx* ctx, const void* share, uint64_t nshare, int weighted, int on_device,
+                   uint32_t nvertices, const gt_graph_flags* flags, int compression, gt_graph** out);
+/* gt_graph_build_rmat with every rank generating records [rank * (nedges / nranks), ...) (the last rank also the
+ * remainder) and routing them as above. */
+GT_API int gt_graph_build_rmat_partitioned(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uint64_t seed, int weighted,
                         const gt_graph_flags* flags, int compression, gt_graph** out);
 GT_API int gt_rmat_generate(gt_ctx* ctx, uint32_t scale, uint64_t first_edge, uint64_t nedges, uint64_t seed,
                      int weighted, void* triples_dev);
@@ -246,6 +260,11 @@ typedef struct {
                                        REG x SNK and source-row entries, as the reference does                                */
 } gt_timing;
 GT_API int gt_program_timing(gt_program* p, gt_timing* out);
+/* The reference's -DTIMING vectors (src/vp/vertex_program.hpp:202-208) for the most recent execute(), with the "timing" knob
+ * on: one wall-clock sample in ms per iteration of phase 0 scatter_gather_time, 1 combine_time, 2 apply_time; phase 3 = the
+ * single init_time sample.  *n = samples available; at most `cap` are written.  display() prints its `TIMING` line from
+ * these (:2134-2152). */
+GT_API int gt_program_timing_samples(gt_program* p, int phase, double* out_ms, uint32_t cap, uint32_t* n);
 /* One phase of one iteration in isolation, for per-phase timing (the reference's -DTIMING counters,
  * src/vp/vertex_program.hpp:640-684,1018-1054,1611-1637): 0 scatter_gather, 1 combine (the SpMV /
  * SpMSpV over every local tile + the row-group reduce), 2 apply.  Does not advance `iteration`. */

@@ -542,3 +542,34 @@ def test_pagerank_cf_schedule_at_scale_20():
         assert (out[E._TCSC_]["degree"] == out[E._TCSC_CF_]["degree"]).all()
         rel = np.abs(out[E._TCSC_]["rank"] - out[E._TCSC_CF_]["rank"]) / out[E._TCSC_]["rank"]
         assert rel.max() <= 1e-12, (iters, rel.max())
+
+
+def test_partitioned_ingest_on_one_rank_is_the_global_build():
+    """gt_graph_build_partitioned with a single rank has nothing to route: same arrays as gt_graph_build (the multi-rank
+    exchange is checked by tools/multi_gpu_check.py on 2/4/8 GPUs), and the timing samples come back per iteration."""
+    E = _E()
+    from graphtap_b200.rmat import rmat_edges
+    tri = rmat_edges(12, seed=5, weighted=True)
+    fl = dict(directed=True, transpose=True, self_loops=False, acyclic=False, parallel_edges=False, compression_type=E._TCSC_)
+    A = E.Graph(weighted=True).load_triples(tri, 1 << 12, **fl)
+    B = E.Graph(weighted=True).load_triples(tri, 1 << 12, partitioned=True, **fl)
+    Cg = E.Graph(weighted=True).load_rmat(12, seed=5, partitioned=True, **fl)
+    ta, tb, tc = A.tile(0), B.tile(0), Cg.tile(0)
+    for f in ("JA", "IA", "A", "JC", "IR"):
+        assert (ta[f] == tb[f]).all() and (ta[f] == tc[f]).all(), f
+    assert A.info().nedges_input == B.info().nedges_input == Cg.info().nedges_input == tri.shape[0]
+    V = E.SSSP_Program(A, False, True, False, E._ROW_)
+    V.set("timing", 1)
+    it = V.execute()
+    n = C.c_uint32()
+    from graphtap_b200.capi import lib, check
+    for phase in (0, 1, 2):
+        buf = (C.c_double * 64)()
+        check(lib().gt_program_timing_samples(V.handle, phase, buf, 64, C.byref(n)))
+        assert n.value == it and all(buf[i] >= 0 for i in range(it))
+        tm = V.timing()
+        total = (tm.scatter_gather_ms, tm.combine_ms, tm.apply_ms)[phase]
+        assert abs(sum(buf[i] for i in range(it)) - total) <= 1e-9 + 1e-9 * total
+    check(lib().gt_program_timing_samples(V.handle, 3, buf, 64, C.byref(n)))
+    assert n.value == 1 and buf[0] > 0
+    V.free(); A.free(); B.free(); Cg.free()

@@ -2,7 +2,8 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 
-Every rank builds its tiles from the same global edge list, runs PR / BFS / CC / SSSP through the C ABI
+Every rank builds its tiles from the same global edge list (and, in the last block, from its 1/p share of it:
+partitioned ingest must give the bit-identical graph), runs PR / BFS / CC / SSSP through the C ABI
 with NCCL exchanges along the reference's row / column groups, and compares its owned segment with the
 CPU oracle simulating the same p (bit-exact for the integer apps, 1e-6 relative for PageRank)."""
 import os
@@ -105,6 +106,61 @@ def main():
     print(f"[rank {rank}/{p}] cc run_phase x3 == execute(3), then execute(): {'OK' if good else 'FAIL'}", flush=True)
     ok &= good
     A.free(); B.free(); G.free()
+    # ---- partitioned ingest (gt_graph_build_partitioned): every rank passes 1/p of the records; the graph must come out
+    # bit-identical to the build where every rank scans the whole list (tiles, maps, CF lists, hot-order-dependent results) ----
+    def graph_fingerprint(G):
+        out, tiles = [], [G.tile(k) for k in range(G.info().ntiles_local)]
+        for t in tiles:
+            out += [t[f] for f in ("JA", "IA", "JC", "IR")] + ([t["A"]] if t["A"] is not None else [])
+        for s_ in sorted({t["row_slot"] for t in tiles}):
+            out += list(G.rowgrp_maps(s_)[:2])
+        for s_ in sorted({t["col_slot"] for t in tiles}):
+            out += list(G.colgrp_maps(s_)[:2])
+        return out
+
+    import tempfile
+    import zlib
+    for name, tri, n, weighted, fl in (
+            ("fixture directed+transpose (pr)", np.fromfile(os.path.join(ROOT, "tests/golden/rmat10_1024.bin"), dtype="<u4").reshape(-1, 2), 1024, False,
+             dict(directed=True, transpose=True, self_loops=True, acyclic=False, parallel_edges=True, compression_type=E._TCSC_CF_)),
+            ("rmat14 undirected dedup (cc)", rmat_edges(14, seed=15, weighted=False), 1 << 14, False,
+             dict(directed=False, transpose=False, self_loops=True, acyclic=False, parallel_edges=False, compression_type=E._TCSC_)),
+            ("rmat14 weighted transpose dedup (sssp)", rmat_edges(14, seed=15, weighted=True), 1 << 14, True,
+             dict(directed=True, transpose=True, self_loops=False, acyclic=False, parallel_edges=False, compression_type=E._TCSC_))):
+        Gg = E.Graph(weighted=weighted).load_triples(tri, n, **fl)
+        # (a) an uneven in-memory split, (b) the reference's split of a binary file, read by byte range
+        cut = [0] + sorted(int(x) for x in np.random.default_rng(7).integers(0, tri.shape[0] + 1, p - 1)) + [tri.shape[0]]
+        Gp = E.Graph(weighted=weighted).load_triples(tri[cut[rank]:cut[rank + 1]], n, partitioned=True, **fl)
+        path = os.path.join(tempfile.gettempdir(), f"gt_check_{os.environ.get('MASTER_PORT', '0')}_{zlib.crc32(name.encode())}.bin")
+        if rank == 0:
+            tri.astype("<u4").tofile(path)
+        E.Env.barrier()
+        Gf = E.Graph(weighted=weighted).load(path, n, n, **fl)           # nranks > 1: partitioned by default
+        a, b, c = graph_fingerprint(Gg), graph_fingerprint(Gp), graph_fingerprint(Gf)
+        good = len(a) == len(b) == len(c) and all(x.shape == y.shape == z.shape and (x == y).all() and (x == z).all() for x, y, z in zip(a, b, c))
+        good &= Gg.info().nnz_global == Gp.info().nnz_global == Gf.info().nnz_global and Gp.info().nedges_input == tri.shape[0] == Gf.info().nedges_input
+        if fl["compression_type"] == E._TCSC_CF_:
+            for k in range(Gg.info().ntiles_local):
+                x, y = Gg.tile_cf(k), Gp.tile_cf(k)
+                good &= all(x[f"{f}{i}"].shape == y[f"{f}{i}"].shape and (x[f"{f}{i}"] == y[f"{f}{i}"]).all() for f in ("JA", "JC") for i in range(4))
+        E.Env.barrier()
+        if rank == 0:
+            os.unlink(path)
+        print(f"[rank {rank}/{p}] partitioned ingest, {name}: {len(a)} arrays, nnz {Gp.info().nnz_local}/{Gp.info().nnz_global} -> {'OK' if good else 'FAIL'}", flush=True)
+        ok &= good
+        Gg.free(); Gp.free(); Gf.free()
+    # generated graph, each rank generating 1/p of the records: same PageRank as the oracle
+    def load_rp(G, **fl):
+        G.load_rmat(13, seed=14, partitioned=True, **fl)
+    G, V = E.run_pr(load_rp, 20)
+    ref, _ = O.run_app("pr", rmat_edges(13, seed=14, weighted=False), 1 << 13, p, 20)
+    lay = G.info().layout
+    mref = ref[lay.owned_segment * lay.tile_height:(lay.owned_segment + 1) * lay.tile_height]
+    rel = np.abs(V.V["rank"] - mref["rank"]) / np.abs(mref["rank"])
+    good = bool(rel.max() <= 1e-6)
+    print(f"[rank {rank}/{p}] partitioned rmat13 pr: max rel {rel.max():.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+    ok &= good
+    V.free(); G.free()
     E.Env.barrier()
     print(f"[rank {rank}] MULTI_GPU_CHECK {'PASS' if ok else 'FAIL'}", flush=True)
     E.Env.finalize()
