@@ -456,17 +456,21 @@ k_ns_apply(VState V, int app, int weighted, uint32_t vid0, const uint32_t* __res
                 if (nw != old) { V.a[v] = nw; ch = true; }
                 msg = nw;                                              // sssp.h:45-47
             }
-            V.C[v] = ch;
             changed += ch;
+            // x[j] != infinity() exactly where C[v] is set (the messenger and every earlier pass keep it so), so a vertex
+            // that was inactive and stays inactive — nearly all of them in the long tail — has nothing to write
+            if (!ch && !V.C[v]) continue;
+            V.C[v] = ch;
             if (J[v]) {                                                // the vertex has a column: next iteration's x (:737-751)
                 const uint32_t j = JV[v];
                 x[j] = ch ? msg : GT_INF_U32;
                 if (ch) { cj[u] = j; cm[u] = msg; mine++; fe += cdeg[v]; }
             }
         }
+        if (!__syncthreads_or(mine != 0)) continue;                    // no new frontier entry in these 1024 rows: no scan
         unsigned off, total;
         BS(tmp).ExclusiveSum(mine, off, total);
-        if (threadIdx.x == 0 && total) base_s = atomicAdd(count, total);
+        if (threadIdx.x == 0) base_s = atomicAdd(count, total);
         __syncthreads();
         if (mine) {
             unsigned pos = base_s + off;

@@ -8,6 +8,7 @@ emits the same stream, tests/test_rmat.py + test_gpu_parity.py::test_device_rmat
   * BFS root 0, RMAT-22            = BASELINE.json configs[1] exactly: parents and hops bit-exact
   * PageRank 20 iterations, RMAT-22: every rank within 1e-6 relative (north_star), degrees exact
   * SSSP root 0, weighted RMAT-22  : distances bit-exact
+  * Connected components, RMAT-22  : labels bit-exact (BASELINE.json configs[4] is the same program at RMAT-27 on 8 GPUs)
 
 The reference runs at np = 16 (or the largest power of two the host offers), the GPU at p = 1: integer
 results are p-independent, PageRank differs by f64 summation order only."""
@@ -56,6 +57,8 @@ def _gpu(app, weighted, arg):
         G, V = E.run_pr(load, arg)
     elif app == "bfs":
         G, V = E.run_bfs(load, arg)
+    elif app == "cc":
+        G, V = E.run_cc(load)
     else:
         G, V = E.run_sssp(load, arg)
     out = V.V, V.iteration, V.checksum(quiet=True), V.timing()
@@ -99,5 +102,15 @@ def test_sssp_rmat22_root0_vs_reference(edge_files):
     n = (1 << SCALE) + 1
     assert it == rit
     m = mine["distance"]
+    assert (m[:n] == ref[:n]).all()
+    assert cs == rcs
+
+
+def test_cc_rmat22_vs_reference(edge_files):
+    ref, rit, rcs = _ref("cc", edge_files[0], None)
+    mine, it, cs, _ = _gpu("cc", False, None)
+    n = (1 << SCALE) + 1
+    assert it == rit
+    m = mine["label"]
     assert (m[:n] == ref[:n]).all()
     assert cs == rcs

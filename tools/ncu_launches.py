@@ -1,8 +1,9 @@
 """Summarise a long-format `ncu --metrics ... --csv --log-file X.csv` launch list: one line per launch (in order) and
-per-kernel totals.  usage: python tools/ncu_launches.py X.csv [--per-launch]"""
+per-kernel totals.  usage: python tools/ncu_launches.py X.csv [--per-launch [--min-us T]]"""
 import csv, sys, collections, re
 path = sys.argv[1]
 per_launch = '--per-launch' in sys.argv
+min_us = float(sys.argv[sys.argv.index('--min-us') + 1]) if '--min-us' in sys.argv else 0.0     # per-launch lines only for launches at least this long
 lines = [l for l in open(path) if l.startswith('"')]
 rows = list(csv.DictReader(lines))
 L = collections.OrderedDict()
@@ -21,7 +22,7 @@ T = sum(d.get('gpu__time_duration.sum', 0) for d in L.values())
 for k, d in L.items():
     us = d.get('gpu__time_duration.sum', 0)
     by = d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0)
-    if per_launch:
+    if per_launch and us >= min_us:
         print(f"{k:4d} {d['name'][:44]:44s} grid {d['grid']:>12s} {us:9.1f} us  dram {by/1e6:9.1f} MB  {by/us/1e3 if us else 0:7.0f} GB/s  "
               f"l1tex {d.get('l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 0):5.1f}%  lts {d.get('lts__throughput.avg.pct_of_peak_sustained_elapsed', 0):5.1f}%  "
               f"dram {d.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 0):5.1f}%")
