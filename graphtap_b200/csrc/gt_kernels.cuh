@@ -152,7 +152,10 @@ spmv_push_chunks(const uint32_t* __restrict__ JA, const uint32_t* __restrict__ I
                     // the filter read goes to L2, one per edge, in line: through L1 (stale lines are safe, y never increases)
                     // and / or with a thread's four reads issued ahead of its REDs it measured 2-7 % slower
                     // (profiles/r02_ns_filter_read_variants.md)
-                    if (t) { if (val < __ldcg(y + rows[k]) && val < atomicMin(y + rows[k], val)) t[rows[k]] = 1; }
+                    // t marks every row a RED went out for: a superset of the rows that improved (all a follower owes its
+                    // leader) and a subset of the reference's touched rows (:1486).  Waiting for the atomic's old value to
+                    // mark only the winners turns every RED into a round trip (ATOM), which is what bounded these passes
+                    if (t) { if (val < __ldcg(y + rows[k])) { atomicMin(y + rows[k], val); t[rows[k]] = 1; } }
                     else SR::reduce_dense(y + rows[k], val);
                 } else {
                     SR::reduce_dense(y + rows[k], val);

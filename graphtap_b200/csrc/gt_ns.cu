@@ -24,9 +24,9 @@
 //     vertex walks its (ascending) neighbour list and stops at the first active one, which IS the minimum parent id
 //     the reference's min-combiner (src/apps/bfs.h:61-63) would leave in y;
 //   * multi-GPU: the owner's SMs store x — list or dense, by the 0.6 rule — into the column group's NVLink peer windows;
-//     partial y travels to the row segment's leader the same way, as the rows that IMPROVED in this iteration (y is a
-//     running minimum that is never reset, :1785-1793, so an unchanged row has nothing new to say) or dense when
-//     more than 60 % did; the leader merges with a scatter-min.  A world all-reduce per iteration (the convergence
+//     partial y travels to the row segment's leader the same way, as the rows a RED went out for in this iteration (y
+//     is a running minimum that is never reset, :1785-1793, so a row whose current value already beats the candidate
+//     has nothing new to say) or dense when more than 60 % did; the leader merges with a scatter-min.  A world all-reduce per iteration (the convergence
 //     count, or a 1-element fence in fixed-iteration mode) orders every rank's next put behind every reader of the
 //     current one, including across execute() / run_phase() calls, so the windows need a single buffer.
 #include "gt_program.h"
@@ -216,8 +216,11 @@ __global__ void k_ns_header(unsigned int* __restrict__ count, uint32_t n, NsRule
 template <int S>
 __device__ __forceinline__ void ns_reduce(typename Semiring<S>::T* y, uint8_t* t, uint32_t r, typename Semiring<S>::T v, bool filter) {
     if (filter && v >= __ldcg(y + r)) return;
-    if (t) { if (v < atomicMin(y + r, v)) t[r] = 1; }      // the row improved in this iteration: it goes to the leader
-    else Semiring<S>::reduce(y + r, v);
+    if (!t) { Semiring<S>::reduce(y + r, v); return; }
+    // the row goes to the leader: with the filter, every row a RED went out for (fire and forget; a superset of the rows
+    // that improved); without it — small frontiers — exactly the rows whose atomic won
+    if (filter) { atomicMin(y + r, v); t[r] = 1; }
+    else if (v < atomicMin(y + r, v)) t[r] = 1;
 }
 
 // frontier SpMSpV over every local tile whose column segment travelled as a list (:1476-1488).

@@ -146,9 +146,10 @@ GT_API int gt_graph_build_rmat(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uin
                         const gt_graph_flags* flags, int compression, gt_graph** out);
 /* Partitioned ingest = the reference's own scheme: every rank passes ITS SHARE of the records (Graph::parread_binary reads
  * bytes [rank*share, ...) of the file, src/mat/graph.hpp:307-335), the per-edge flags run on the share and every entry
- * travels to the rank that owns its tile (Matrix::distribute's pairwise Sendrecv, src/mat/matrix.hpp:692-810, as one
- * grouped NCCL send/recv exchange); the non-empty row/column marks and degrees are all-reduced (the reference OR-reduces
- * them along the row/column groups, :973-1083).  Any split of the global list gives the same graph as gt_graph_build on
+ * travels to the rank that owns its tile (Matrix::distribute's pairwise Sendrecv rounds, src/mat/matrix.hpp:692-810, as
+ * copies into the owners' NVLink peer windows, or one grouped NCCL send/recv exchange where the ranks cannot map each
+ * other); the non-empty row/column marks and degrees are all-reduced (the reference OR-reduces them along the
+ * row/column groups, :973-1083).  Any split of the global list gives the same graph as gt_graph_build on
  * the whole list: tiles, maps and orders are bit-identical.  Collective over the context's ranks; with one rank it is
  * gt_graph_build.  nedges_input of the result = records over all shares. */
 GT_API int gt_graph_build_partitioned(gt_ctx* ctx, const void* share, uint64_t nshare, int weighted, int on_device,
