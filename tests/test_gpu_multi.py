@@ -1,6 +1,7 @@
-"""Multi-GPU parity (NCCL exchange along the reference's row/column groups): tools/multi_gpu_check.py under
-torchrun on every GPU count the box offers.  Skipped on a single-GPU box; the CPU-side plan is covered by
-tests/test_dist_cpu.py, and profiles/r01_multi_gpu_check_p8.log records the 8-GPU run."""
+"""Multi-GPU parity (peer-window / NCCL exchange along the reference's row/column groups, partitioned ingest):
+tools/multi_gpu_check.py under torchrun on every GPU count the box offers.  Skipped on a single-GPU box; the CPU-side
+plan is covered by tests/test_dist_cpu.py and tests/test_peer_protocol.py, profiles/r02_multi_gpu_check_p{2,4,8}.log record
+the runs, and bench.py repeats a parity block at every N > 1 (`multi_gpu_parity`)."""
 import os
 import subprocess
 import sys
