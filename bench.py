@@ -255,6 +255,17 @@ def golden_parity(E, red):
             "against": "tests/golden/{fixture,rmat12_seed12}.npz = per-vertex dumps of the unmodified reference (np=1); integer apps bit-exact, PageRank <= 1e-6"}
 
 
+def hbm_used_gb():
+    """Device memory in use on this rank's GPU (nvidia-smi's view: every allocation incl. the CUDA contexts); None if unavailable."""
+    try:
+        idx = os.environ.get("LOCAL_RANK", "0")
+        out = subprocess.run(["nvidia-smi", "--query-gpu=memory.used", "--format=csv,noheader,nounits", "-i", idx],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        return float(out) * 1.048576e-3          # MiB -> GB
+    except Exception:
+        return -1.0
+
+
 def other_config(E, red, app, scale, peak, runs=3):
     """One of BASELINE.json configs[1,3,4]: device-timed execute() (the reference's "Execute time" window) of a
     non-stationary program on synthetic RMAT, the mean of `runs` runs after one warm-up run."""
@@ -280,6 +291,7 @@ def other_config(E, red, app, scale, peak, runs=3):
             ms.append(tm.execute_ms)
         if r == runs:
             cs = V.checksum(quiet=True)
+            used = red.max(hbm_used_gb())          # graph + program resident: the footprint of the config per GPU
         V.free()
         E.Env.barrier()
     nnz = G.info().nnz_global
@@ -291,7 +303,8 @@ def other_config(E, red, app, scale, peak, runs=3):
     return {"workload": f"{name} synthetic RMAT scale-{scale} (ef=16)", "n_gpus": n, "execute_ms": t * 1e3, "iterations": int(it),
             "sparse_iterations": int(tm.sparse_iterations), "nnz": int(nnz), "gteps": nnz / t / 1e9,
             "bytes_algorithmic": int(bytes_all), "achieved_gbs": bytes_all / t / 1e9, "frac": bytes_all / t / 1e9 / (peak * n),
-            "checksum": [int(cs[0]), int(cs[1])], "build_seconds": round(build_s, 2), "kernel_launches": int(tm.kernel_launches)}
+            "checksum": [int(cs[0]), int(cs[1])], "build_seconds": round(build_s, 2), "kernel_launches": int(tm.kernel_launches),
+            "hbm_used_gb_per_gpu": round(used, 2) if used >= 0 else None}
 
 
 def run_ours(args):
@@ -323,6 +336,7 @@ def run_ours(args):
     P.initialize(D)
     E.Env.barrier()
     t_build = time.time() - t_build
+    hbm_used = red.max(hbm_used_gb())                     # tiles + pull layout + vectors + windows: everything the path keeps resident
 
     # ---- value: resident inputs, device-timed ----------------------------------------------------------
     sampler = None
@@ -450,7 +464,8 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(scale), "nnz": int(nnz), "vertices": 1 << scale, "iterations_per_step": ITERS,
                        "parallelism": f"2dt-p{nranks}", "l2": "inputs (>= 4 GB of IA per pass) exceed the 126 MB L2, no flush needed",
-                       "build_seconds": round(t_build, 2), "rank_sum_global": rank_sum, "rank_sqsum_global": rank_sqsum},
+                       "build_seconds": round(t_build, 2), "rank_sum_global": rank_sum, "rank_sqsum_global": rank_sqsum,
+                       "hbm_used_gb_per_gpu": round(hbm_used, 2) if hbm_used >= 0 else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "other_configs": others,
         }

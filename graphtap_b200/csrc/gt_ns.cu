@@ -178,19 +178,22 @@ __global__ void __launch_bounds__(256) k_ns_put_x(const uint32_t* __restrict__ d
         if (mode == NS_SPARSE) { copy_u32(T.xi[j], xi, k, tid, nth); copy_u32(T.xv[j], xv, k, tid, nth); }
         else copy_u32(T.dense[j], dense, n, tid, nth);
     }
-    __threadfence_system();
     __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(done, 1u) == nblk - 1;
-    __syncthreads();
-    if (!last) return;                             // the last CTA to finish publishes: every payload store is ordered before
-    __threadfence_system();
+    if (T.n) {                                     // (one GPU: a single CTA and nothing to order)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(done, 1u) == nblk - 1;
+        __syncthreads();
+        if (!last) return;                         // the last CTA to finish publishes: every payload store is ordered before
+        __threadfence_system();
+    }
     if (threadIdx.x == 0) {
         own_hdr[0] = mode; own_hdr[1] = k; *done = 0;
         *count = 0; *frontier_edges = 0; *next_active = 0;      // what this iteration's applicator accumulates into
         // the (all-reduced) active count of the previous iteration goes straight to the pinned host word the convergence
-        // check reads: no device-to-host copy sits between an iteration's all-reduce and the next iteration's first kernel
-        if (host_prev) { *host_prev = *prev_active; __threadfence_system(); }
+        // check reads (visible to the host once this kernel has completed, which is what its event waits for): no
+        // device-to-host copy sits between an iteration's all-reduce and the next iteration's first kernel
+        if (host_prev) *host_prev = *prev_active;
     }
     if ((int) threadIdx.x < T.n) {
         volatile uint32_t* h = T.hdr[threadIdx.x];
