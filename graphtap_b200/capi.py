@@ -92,6 +92,8 @@ PROTOTYPES = {
     "gt_graph_build_rmat": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
     "gt_graph_build_partitioned": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
     "gt_graph_build_rmat_partitioned": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(GraphFlags), C.c_int, C.POINTER(C.c_void_p)]),
+    "gt_ingest_route_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gt_rmat_generate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]),
     "gt_graph_free": (C.c_int, [C.c_void_p]),
     "gt_graph_info_get": (C.c_int, [C.c_void_p, C.POINTER(GraphInfo)]),

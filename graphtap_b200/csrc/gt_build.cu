@@ -639,19 +639,18 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
         comm_allreduce(ctx->comm, COMM_WORLD, cdeg_all.p, cdeg_all.p, nall, CT_U32, CO_SUM, st);
         comm_allreduce(ctx->comm, COMM_WORLD, counters.p + 2, counters.p + 2, 1, CT_U64, CO_SUM, st);
         GT_CUDA(cudaStreamSynchronize(st));
-        std::vector<uint64_t> scount(nr), sdispl(nr), rcount(nr), rdispl(nr);
-        std::vector<unsigned long long> h_off(nr);
-        uint64_t nsend = 0, nrecv = 0, nrecords = 0;
-        const uint64_t rec_bytes = rec_words * 4;
-        for (int q = 0; q < nr; q++) {
-            const uint64_t s_q = h_matrix[(size_t) ctx->rank * (nr + 1) + q], r_q = h_matrix[(size_t) q * (nr + 1) + ctx->rank];
-            h_off[q] = nsend;
-            scount[q] = s_q * rec_bytes; sdispl[q] = nsend * rec_bytes; nsend += s_q;
-            rcount[q] = r_q * rec_bytes; rdispl[q] = nrecv * rec_bytes; nrecv += r_q;
-            nrecords += h_matrix[(size_t) q * (nr + 1) + nr];
+        // the plan (host arithmetic, gt_layout.cpp; entries -> bytes here)
+        std::vector<uint64_t> cmat((size_t) nr * nr);
+        uint64_t nrecords = 0;
+        for (int r = 0; r < nr; r++) {
+            for (int q = 0; q < nr; q++) cmat[(size_t) r * nr + q] = h_matrix[(size_t) r * (nr + 1) + q];
+            nrecords += h_matrix[(size_t) r * (nr + 1) + nr];
         }
+        const RoutePlan plan = make_route_plan(nr, ctx->rank, cmat.data());
+        const uint64_t rec_bytes = rec_words * 4, nrecv = plan.nrecv;
+        std::vector<unsigned long long> h_off(plan.send_offset.begin(), plan.send_offset.end());
         g->nedges_input = nrecords;
-        DevBuf<uint32_t> sendbuf; sendbuf.alloc(std::max<uint64_t>(nsend, 1) * rec_words);
+        DevBuf<uint32_t> sendbuf; sendbuf.alloc(std::max<uint64_t>(plan.nsend, 1) * rec_words);
         GT_CUDA(cudaMemcpyAsync(dest_off.p, h_off.data(), (size_t) nr * 8, cudaMemcpyHostToDevice, st));
         GT_CUDA(cudaMemsetAsync(dest_count.p, 0, (size_t) nr * 8, st));
         Q.sendbuf = sendbuf.p;
@@ -659,29 +658,28 @@ static gt_graph* build(gt_ctx* ctx, const void* triples, uint64_t ntriples, int 
         // The exchange.  Where the ranks can map each other's memory (one node, NVLink), every rank copies its blocks straight
         // into the owners' receive buffers — a world peer window sized for the largest receiver — and one world fence tells
         // everybody that all copies have landed; a block from rank r sits behind the blocks of the ranks before r, the
-        // order the receive displacements assume.  No NCCL point-to-point connections are built (the first grouped
-        // send/recv of a job costs ~7 s at 8 ranks).  Otherwise: one grouped ncclSend/ncclRecv exchange.
-        uint64_t max_recv = 0;
-        for (int q = 0; q < nr; q++) {
-            uint64_t tot = 0;
-            for (int r = 0; r < nr; r++) tot += h_matrix[(size_t) r * (nr + 1) + q];
-            max_recv = std::max(max_recv, tot);
-        }
+        // order the receive offsets assume.  No NCCL point-to-point connections are built (the first grouped
+        // send/recv of a job costs ~6 s at 4-8 ranks).  Otherwise: one grouped ncclSend/ncclRecv exchange.
         const char* pe = getenv("GT_PEER");
-        route_win = (pe && atoi(pe) == 0) ? nullptr : peer_window_create(ctx, COMM_WORLD, std::max<uint64_t>(max_recv, 1) * rec_bytes);
+        route_win = (pe && atoi(pe) == 0) ? nullptr : peer_window_create(ctx, COMM_WORLD, std::max<uint64_t>(plan.max_recv, 1) * rec_bytes);
         const uint32_t* received = nullptr;
+        auto mine = [&](int q) { return cmat[(size_t) ctx->rank * nr + q] * rec_bytes; };      // bytes this rank holds for q
         if (route_win) {
             for (int j = 0; j < nr; j++) {
                 const int q = (ctx->rank + j) % nr;                    // start with the own block, then walk the ring
-                if (!scount[q]) continue;
-                uint64_t before = 0;
-                for (int r = 0; r < ctx->rank; r++) before += h_matrix[(size_t) r * (nr + 1) + q];
-                GT_CUDA(cudaMemcpyAsync(route_win->remote[q] + before * rec_bytes, (const uint8_t*) sendbuf.p + sdispl[q], scount[q], cudaMemcpyDefault, st));
+                if (!mine(q)) continue;
+                GT_CUDA(cudaMemcpyAsync(route_win->remote[q] + plan.remote_offset[q] * rec_bytes, (const uint8_t*) sendbuf.p + plan.send_offset[q] * rec_bytes,
+                                        mine(q), cudaMemcpyDefault, st));
             }
             peer_fence_world(ctx, st);
             received = (const uint32_t*) route_win->local;
         } else {
             routed.alloc(std::max<uint64_t>(nrecv, 1) * rec_words);
+            std::vector<uint64_t> scount(nr), sdispl(nr), rcount(nr), rdispl(nr);
+            for (int q = 0; q < nr; q++) {
+                scount[q] = mine(q); sdispl[q] = plan.send_offset[q] * rec_bytes;
+                rcount[q] = cmat[(size_t) q * nr + ctx->rank] * rec_bytes; rdispl[q] = plan.recv_offset[q] * rec_bytes;
+            }
             if (scount[ctx->rank])
                 GT_CUDA(cudaMemcpyAsync((uint8_t*) routed.p + rdispl[ctx->rank], (const uint8_t*) sendbuf.p + sdispl[ctx->rank], scount[ctx->rank], cudaMemcpyDeviceToDevice, st));
             scount[ctx->rank] = rcount[ctx->rank] = 0;

@@ -101,6 +101,13 @@ struct Layout {
     }
 };
 Layout make_layout(uint32_t nvertices, int nranks, int rank);
+struct RoutePlan {                               // partitioned ingest: where this rank's blocks go (entries, not bytes)
+    std::vector<uint64_t> send_offset;           // [nranks] first entry of the block for q in my send buffer
+    std::vector<uint64_t> recv_offset;           // [nranks] first entry of the block from q in my receive buffer
+    std::vector<uint64_t> remote_offset;         // [nranks] first entry of MY block in q's receive buffer
+    uint64_t nsend = 0, nrecv = 0, max_recv = 0; // my totals; the largest receive buffer of any rank
+};
+RoutePlan make_route_plan(int nranks, int rank, const uint64_t* counts);
 
 // ---- NCCL through dlopen (gt_comm.cpp) -------------------------------------------------------------
 struct Comm;   // opaque: world + row-group + col-group communicators

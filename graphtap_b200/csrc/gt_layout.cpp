@@ -95,7 +95,43 @@ Layout make_layout(uint32_t nvertices, int nranks, int rank) {
     return L;
 }
 
+// The exchange plan of a partitioned ingest (gt_build.cu) for one rank, from the world's count matrix
+// counts[r * nranks + q] = entries rank r holds for rank q.  Blocks sit in destination order in the send buffer and in
+// sender order in every receive buffer — so a block from `rank` lands in q's buffer behind the blocks of the ranks
+// before it, which is where q's own plan expects it.  Host arithmetic only.
+RoutePlan make_route_plan(int nranks, int rank, const uint64_t* counts) {
+    RoutePlan P;
+    P.send_offset.assign(nranks, 0); P.recv_offset.assign(nranks, 0); P.remote_offset.assign(nranks, 0);
+    for (int q = 0; q < nranks; q++) {
+        P.send_offset[q] = P.nsend; P.nsend += counts[(size_t) rank * nranks + q];
+        P.recv_offset[q] = P.nrecv; P.nrecv += counts[(size_t) q * nranks + rank];
+        uint64_t col = 0;
+        for (int r = 0; r < nranks; r++) {
+            if (r == rank) P.remote_offset[q] = col;
+            col += counts[(size_t) r * nranks + q];
+        }
+        P.max_recv = std::max(P.max_recv, col);
+    }
+    return P;
+}
+
 }  // namespace gt
+
+extern "C" int gt_ingest_route_plan(int nranks, int rank, const uint64_t* counts, uint64_t* send_offset, uint64_t* recv_offset,
+                                    uint64_t* remote_offset, uint64_t* nsend, uint64_t* nrecv, uint64_t* max_recv) {
+    return gt::guarded([&] {
+        GT_REQUIRE(counts && nranks >= 1 && rank >= 0 && rank < nranks, "gt_ingest_route_plan: bad arguments");
+        const gt::RoutePlan P = gt::make_route_plan(nranks, rank, counts);
+        for (int q = 0; q < nranks; q++) {
+            if (send_offset) send_offset[q] = P.send_offset[q];
+            if (recv_offset) recv_offset[q] = P.recv_offset[q];
+            if (remote_offset) remote_offset[q] = P.remote_offset[q];
+        }
+        if (nsend) *nsend = P.nsend;
+        if (nrecv) *nrecv = P.nrecv;
+        if (max_recv) *max_recv = P.max_recv;
+    });
+}
 
 extern "C" int gt_layout_query(uint32_t nvertices, int nranks, int rank, gt_layout* out) {
     return gt::guarded([&] {

@@ -158,6 +158,13 @@ GT_API int gt_graph_build_partitioned(gt_ctx* ctx, const void* share, uint64_t n
  * remainder) and routing them as above. */
 GT_API int gt_graph_build_rmat_partitioned(gt_ctx* ctx, uint32_t scale, uint64_t nedges, uint64_t seed, int weighted,
                         const gt_graph_flags* flags, int compression, gt_graph** out);
+/* The exchange plan gt_graph_build_partitioned follows, as host arithmetic (callable without a GPU; tests/test_ingest_share.py
+ * drives it over gloo): counts[r * nranks + q] = entries rank r holds for rank q (what Matrix::distribute's Sendrecv
+ * rounds exchange pairwise, src/mat/matrix.hpp:692-810).  Per destination / source q: where the block for q starts in this
+ * rank's send buffer, where the block from q starts in its receive buffer, and where this rank's block starts in q's
+ * receive buffer (blocks lie in sender order); totals, and the largest receive buffer of any rank.  Units: entries. */
+GT_API int gt_ingest_route_plan(int nranks, int rank, const uint64_t* counts, uint64_t* send_offset, uint64_t* recv_offset,
+                         uint64_t* remote_offset, uint64_t* nsend, uint64_t* nrecv, uint64_t* max_recv);
 GT_API int gt_rmat_generate(gt_ctx* ctx, uint32_t scale, uint64_t first_edge, uint64_t nedges, uint64_t seed,
                      int weighted, void* triples_dev);
 GT_API int gt_graph_free(gt_graph* g);
